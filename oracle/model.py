@@ -1,0 +1,272 @@
+"""Oracle (TEST INFRASTRUCTURE ONLY): numpy restatement of the rnn_ctc deployment graph.
+
+PARITY UNPINNED for this file: TensorFlow 1.x / librosa are absent (see
+oracle/__init__.py).  Every function cites the reference lines it follows.
+
+All functions take ``dtype`` -- ``np.float32`` reproduces the reference's fp32
+graph (every intermediate rounded to fp32 like TF's CPU kernels),
+``np.float64`` is the high-precision master used to bound rounding noise.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+# constants of the shipped deployment config (config/rnn_config.py:57-65,76-84)
+SAMPLE_RATE = 16000
+FFT_SIZE = 400
+HOP_SIZE = 160
+FMIN = 300.0
+FMAX = 8000.0
+HIDDEN = 128
+NUM_LAYERS = 2
+NUM_CLASSES = 6
+N_BINS = FFT_SIZE // 2 + 1
+
+
+# --------------------------------------------------------------------------
+# mel filterbank: librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) with its
+# defaults of that era (htk=False -> Slaney scale, norm=1 -> area normalised).
+# Call sites: models/rnn_ctc.py:139-144, detector.py:126-129, reader.py:33-38.
+# librosa is a third-party dependency that is not vendored and not pinned by
+# the reference (no requirements file); this restates its published algorithm.
+# --------------------------------------------------------------------------
+def _hz_to_mel_slaney(f):
+    f = np.asarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3.0
+    mels = f / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        log_part = min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep
+    return np.where(f >= min_log_hz, log_part, mels)
+
+
+def _mel_to_hz_slaney(m):
+    m = np.asarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3.0
+    freqs = f_sp * m
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), freqs)
+
+
+def slaney_mel_basis(sr=SAMPLE_RATE, n_fft=FFT_SIZE, n_mels=40, fmin=FMIN, fmax=FMAX):
+    """``librosa.filters.mel`` -> ``[n_mels, 1 + n_fft//2]`` float64."""
+    n_bins = 1 + n_fft // 2
+    fftfreqs = np.linspace(0.0, float(sr) / 2.0, n_bins)
+    mel_pts = np.linspace(_hz_to_mel_slaney(fmin), _hz_to_mel_slaney(fmax), n_mels + 2)
+    mel_f = _mel_to_hz_slaney(mel_pts)
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    weights = np.zeros((n_mels, n_bins), dtype=np.float64)
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        weights[i] = np.maximum(0.0, np.minimum(lower, upper))
+    enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
+    weights *= enorm[:, None]
+    return weights
+
+
+# --------------------------------------------------------------------------
+# weights container (layout == the TF variables' own layout)
+# --------------------------------------------------------------------------
+@dataclass
+class Weights:
+    """rnn_ctc deployment parameters in the TF checkpoint layout.
+
+    ``gates_kernel[l]``: ``[in_l + H, 2H]`` rows = concat(x, h), cols = r | u
+    ``cand_kernel[l]`` : ``[in_l + H, H]``  rows = concat(x, r*h)
+    ``fc_w``           : ``[H, C]`` (weightsClasses), ``fc_b``: ``[C]``
+    ``mel_basis``      : ``[201, M]`` (= librosa mel(...).T, rnn_ctc.py:139-146)
+    """
+    mel_basis: np.ndarray
+    gates_kernel: List[np.ndarray] = field(default_factory=list)
+    gates_bias: List[np.ndarray] = field(default_factory=list)
+    cand_kernel: List[np.ndarray] = field(default_factory=list)
+    cand_bias: List[np.ndarray] = field(default_factory=list)
+    fc_w: np.ndarray = None
+    fc_b: np.ndarray = None
+
+    @property
+    def n_mel(self):
+        return self.mel_basis.shape[1]
+
+    @property
+    def hidden(self):
+        return self.fc_w.shape[0]
+
+    @property
+    def num_layers(self):
+        return len(self.gates_kernel)
+
+    @property
+    def num_classes(self):
+        return self.fc_w.shape[1]
+
+
+def init_weights(seed=1234, n_mel=40, hidden=HIDDEN, num_layers=NUM_LAYERS,
+                 num_classes=NUM_CLASSES, fc_std=1.0) -> Weights:
+    """Random-init weights of the reference architecture.
+
+    GRU kernels Xavier-normal (models/rnn_ctc.py:230-232), gate bias 1.0 and
+    candidate bias 0.0 (TF GRUCell defaults), FC truncated-normal(std 1) clipped
+    at 2 sigma and zero bias (models/rnn_ctc.py:265-273).
+    """
+    rng = np.random.default_rng(seed)
+    w = Weights(mel_basis=slaney_mel_basis(n_mels=n_mel).T.astype(np.float32))
+    for layer in range(num_layers):
+        fan_in = (n_mel if layer == 0 else hidden) + hidden
+        std_g = np.sqrt(2.0 / (fan_in + 2 * hidden))
+        std_c = np.sqrt(2.0 / (fan_in + hidden))
+        w.gates_kernel.append((rng.standard_normal((fan_in, 2 * hidden)) * std_g).astype(np.float32))
+        w.gates_bias.append(np.ones(2 * hidden, dtype=np.float32))
+        w.cand_kernel.append((rng.standard_normal((fan_in, hidden)) * std_c).astype(np.float32))
+        w.cand_bias.append(np.zeros(hidden, dtype=np.float32))
+    fc = rng.standard_normal((hidden, num_classes))
+    bad = np.abs(fc) > 2.0
+    while bad.any():                     # truncated_normal resamples beyond 2 sigma
+        fc[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(fc) > 2.0
+    w.fc_w = (fc * fc_std).astype(np.float32)
+    w.fc_b = np.zeros(num_classes, dtype=np.float32)
+    return w
+
+
+# --------------------------------------------------------------------------
+# front end
+# --------------------------------------------------------------------------
+def num_frames(signal_length: int, frame_length=FFT_SIZE, frame_step=HOP_SIZE) -> int:
+    """utils/stft.py:60-61 -- ``1 + floor((L - frame_length) / frame_step)``."""
+    return 1 + int(np.floor((signal_length - frame_length) / frame_step))
+
+
+def frame(signal: np.ndarray, frame_length=FFT_SIZE, frame_step=HOP_SIZE) -> np.ndarray:
+    """utils/stft.py:27-81 ``tf_frame``: ``[S, L] -> [S, n, frame_length]``.
+
+    Rectangular window, no centring, no padding; the tail that does not fill a
+    frame is dropped.
+    """
+    signal = np.asarray(signal)
+    if signal.ndim != 2:
+        raise ValueError("expected signal to have rank 2 but was %d" % signal.ndim)
+    n = num_frames(signal.shape[1], frame_length, frame_step)
+    if n <= 0:
+        return np.zeros((signal.shape[0], 0, frame_length), dtype=signal.dtype)
+    idx = np.arange(frame_length)[None, :] + frame_step * np.arange(n)[:, None]
+    return signal[:, idx]
+
+
+def linearspec(frames: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """models/rnn_ctc.py:137 -- ``abs(rfft(frames, [400]))`` -> ``[S, n, 201]``."""
+    spec = np.fft.rfft(frames.astype(dtype), n=FFT_SIZE, axis=-1)
+    return np.abs(spec).astype(dtype)
+
+
+def melspec(lin: np.ndarray, mel_basis: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """models/rnn_ctc.py:139-149 -- ``linearspec @ mel_basis[201, M]``."""
+    return np.matmul(lin.astype(dtype), mel_basis.astype(dtype)).astype(dtype)
+
+
+def pcm_to_mel(pcm: np.ndarray, w: Weights, dtype=np.float32) -> np.ndarray:
+    """PCM ``[S, L]`` (float, already scaled by 2^-15) -> mel ``[S, n, M]``."""
+    return melspec(linearspec(frame(pcm), dtype), w.mel_basis, dtype)
+
+
+# --------------------------------------------------------------------------
+# GRU (TF 1.x GRUCell / MultiRNNCell / dynamic_rnn semantics)
+# call sites: models/rnn_ctc.py:179-199 (get_cell), :228-244 (inference1)
+# --------------------------------------------------------------------------
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def gru_cell(x, h, gates_kernel, gates_bias, cand_kernel, cand_bias, dtype=np.float32):
+    """One TF GRUCell step.  NOTE reset gate is applied to h BEFORE the
+    candidate matmul (not the cuDNN / torch.nn.GRU formulation)."""
+    one = dtype(1.0)
+    xh = np.concatenate([x, h], axis=1)
+    gate_in = (np.matmul(xh, gates_kernel.astype(dtype)) + gates_bias.astype(dtype)).astype(dtype)
+    gates = _sigmoid(gate_in).astype(dtype)
+    H = h.shape[1]
+    r, u = gates[:, :H], gates[:, H:]
+    xrh = np.concatenate([x, (r * h).astype(dtype)], axis=1)
+    cand = (np.matmul(xrh, cand_kernel.astype(dtype)) + cand_bias.astype(dtype)).astype(dtype)
+    c = np.tanh(cand).astype(dtype)
+    return (u * h + (one - u) * c).astype(dtype)
+
+
+def gru_forward(x: np.ndarray, state: np.ndarray, w: Weights,
+                seq_len: Optional[np.ndarray] = None, dtype=np.float32
+                ) -> Tuple[np.ndarray, np.ndarray]:
+    """``inference1`` (models/rnn_ctc.py:202-244).
+
+    x ``[S, n, M]``, state ``[layers, S, H]`` -> outputs ``[S, n, H]`` of the
+    last layer, final state ``[layers, S, H]``.  ``seq_len`` follows
+    ``dynamic_rnn(sequence_length=...)``: for ``t >= seq_len[s]`` the output is
+    zero and the state is copied through.
+    """
+    x = x.astype(dtype)
+    S, n, _ = x.shape
+    h = [state[l].astype(dtype).copy() for l in range(w.num_layers)]
+    out = np.zeros((S, n, w.hidden), dtype=dtype)
+    for t in range(n):
+        inp = x[:, t, :]
+        live = None if seq_len is None else (t < np.asarray(seq_len))[:, None]
+        for l in range(w.num_layers):
+            new_h = gru_cell(inp, h[l], w.gates_kernel[l], w.gates_bias[l],
+                             w.cand_kernel[l], w.cand_bias[l], dtype)
+            if live is not None:
+                new_h = np.where(live, new_h, h[l])
+            h[l] = new_h
+            inp = new_h
+        out[:, t, :] = inp if live is None else np.where(live, inp, dtype(0))
+    return out, np.stack(h, axis=0)
+
+
+def fc_logits(rnn_out: np.ndarray, w: Weights, dtype=np.float32) -> np.ndarray:
+    """``inference2`` (models/rnn_ctc.py:247-284); relu/clip branch is dead
+    because ``use_relu`` ends up False (config/rnn_config.py:83)."""
+    S, n, H = rnn_out.shape
+    flat = rnn_out.reshape(-1, H).astype(dtype)
+    logits = (np.matmul(flat, w.fc_w.astype(dtype)) + w.fc_b.astype(dtype)).astype(dtype)
+    return logits.reshape(S, n, -1)
+
+
+def softmax(logits: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """``tf.nn.softmax`` over the last axis (models/rnn_ctc.py:165)."""
+    z = logits.astype(dtype)
+    z = z - z.max(axis=-1, keepdims=True)
+    e = np.exp(z).astype(dtype)
+    return (e / e.sum(axis=-1, keepdims=True)).astype(dtype)
+
+
+def mel_forward(mel: np.ndarray, state: np.ndarray, w: Weights, seq_len=None, dtype=np.float32):
+    """(mel frames, rnn_state) -> (softmax, rnn_state, logits); the commented
+    mel-input form of the deployment graph (models/rnn_ctc.py:150-153)."""
+    out, new_state = gru_forward(mel, state, w, seq_len, dtype)
+    logits = fc_logits(out, w, dtype)
+    return softmax(logits, dtype), new_state, logits
+
+
+def deploy_forward(pcm: np.ndarray, state: np.ndarray, w: Weights, dtype=np.float32):
+    """``DeployModel`` (models/rnn_ctc.py:113-166) batched over streams.
+
+    pcm ``[S, L]`` float (or ``[L]``, the reference's batch-1 form), state
+    ``[layers, S, H]`` -> softmax ``[S, n, C]``, state, logits ``[S, n, C]``.
+    """
+    pcm = np.asarray(pcm)
+    if pcm.ndim == 1:
+        pcm = pcm[None, :]
+    mel = pcm_to_mel(pcm.astype(dtype), w, dtype)
+    return mel_forward(mel, state, w, None, dtype)
+
+
+def pcm16_to_float(x: np.ndarray) -> np.ndarray:
+    """detector.py:40-43 ``buf_to_float`` -- int16 LE PCM -> float32 * 2^-15."""
+    return (np.float32(1.0 / 32768.0) * np.asarray(x, dtype=np.int16).astype(np.float32)).astype(np.float32)

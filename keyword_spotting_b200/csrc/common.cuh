@@ -1,0 +1,118 @@
+// Shared internals of libkws_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/kws_b200.h"
+
+namespace kws {
+
+constexpr int kHidden = 128;      // config/rnn_config.py:84 -- the kernels are built for H = 128
+constexpr int kMaxLayers = 4;
+constexpr int kMaxClasses = 16;
+constexpr int kFft = 400;         // config/rnn_config.py:57
+constexpr int kHop = 160;         // config/rnn_config.py:58
+constexpr int kBins = kFft / 2 + 1;
+constexpr int kMaxMel = 128;
+
+// -------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+void clear_error();
+int fail(int code, const char* fmt, ...);
+
+#define KWS_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::kws::fail(KWS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                         __FILE__, __LINE__);                                               \
+  } while (0)
+
+#define KWS_LAUNCH_OK(what)                                                                 \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      return ::kws::fail(KWS_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define KWS_REQUIRE(cond, ...)                                          \
+  do {                                                                  \
+    if (!(cond)) return ::kws::fail(KWS_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int sm_count();   // SMs of the current device (cached)
+
+// -------------------------------------------------------------------- model
+struct LayerWeights {
+  int in_dim = 0;               // n_mel for layer 0, H above
+  float* gates_kernel = nullptr;  // [in+H, 2H] row-major (TF layout)
+  float* gates_bias = nullptr;    // [2H]
+  float* cand_kernel = nullptr;   // [in+H, H]
+  float* cand_bias = nullptr;     // [H]
+};
+
+struct MelSparse {               // per-band non-zero bin range of the mel basis
+  int* start = nullptr;          // [M]
+  int* count = nullptr;          // [M]
+  int* offset = nullptr;         // [M] into `weight`
+  float* weight = nullptr;       // [nnz] band-major
+  int nnz = 0;
+  int max_count = 0;
+};
+
+}  // namespace kws
+
+struct kws_model {
+  kws_model_config cfg;
+  int device = 0;
+  float* mel_basis = nullptr;     // [201, M] dense, as given
+  kws::MelSparse mel;
+  float2* twiddle400 = nullptr;   // [400] exp(-2*pi*i*k/400)
+  kws::LayerWeights layer[kws::kMaxLayers];
+  float* fc_w = nullptr;          // [H, C]
+  float* fc_b = nullptr;          // [C]
+  // scratch owned by the model (grown by kws_model_reserve)
+  int64_t cap_streams = 0;
+  int32_t cap_frames = 0;
+  float* scratch_mel = nullptr;   // [S, n, M]
+  float* scratch_seq = nullptr;   // layer hand-off [tiles, n, H, 64]
+};
+
+namespace kws {
+
+// ---- kernels' host launchers (one per .cu file)
+struct PcmSource {
+  // sample i of stream s:  i < head_len(s) ? head[s*ld_head + i] : body[s*ld_body + i - head_len(s)]
+  const void* body = nullptr;
+  int64_t ld_body = 0;
+  int32_t body_len = 0;
+  int body_dtype = KWS_PCM_F32;
+  const int16_t* head = nullptr;      // carried tail (server only), int16
+  int64_t ld_head = 0;
+  const int32_t* head_len = nullptr;  // [S] or null (= 0)
+};
+
+int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t max_frames,
+                    const int32_t* nframes /*[S] or null*/, float* mel_out, cudaStream_t st);
+
+struct GruArgs {
+  const float* x = nullptr;       // layer-0 input [S, n, M] row-major
+  int64_t S = 0;
+  int32_t n = 0;
+  const int32_t* seq_len = nullptr;       // [S] or null
+  const uint8_t* zero_state = nullptr;    // [S] or null: 1 = treat incoming state as zero
+  const float* state_in = nullptr;        // [layers, S, H]
+  float* state_out = nullptr;             // [layers, S, H]
+  float* probs = nullptr;                 // [S, n, C]
+  float* logits = nullptr;                // [S, n, C] or null
+};
+int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st);
+
+}  // namespace kws

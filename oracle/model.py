@@ -235,7 +235,7 @@ def fc_logits(rnn_out: np.ndarray, w: Weights, dtype=np.float32) -> np.ndarray:
     S, n, H = rnn_out.shape
     flat = rnn_out.reshape(-1, H).astype(dtype)
     logits = (np.matmul(flat, w.fc_w.astype(dtype)) + w.fc_b.astype(dtype)).astype(dtype)
-    return logits.reshape(S, n, -1)
+    return logits.reshape(S, n, w.fc_w.shape[1])
 
 
 def softmax(logits: np.ndarray, dtype=np.float32) -> np.ndarray:

@@ -110,14 +110,20 @@ def octbit_mat_mul(x, w, transpose_a=False, transpose_b=True, scale=0.0, bias=(0
 
 
 def octize_weight_int8_signed(weight: np.ndarray):
-    """octbit/octbit_graph.py:191-215.  W ``[in,out]`` float ->
+    """octbit/octbit_graph.py:191-215.  W ``[in,out]`` float32 ->
     ``(W_q^T int8 [out,in], scale float64, bias float64 [out])`` with
     ``scale = max|W|/127``, ``W_q = np.round(W/scale)`` (half-to-even) and
-    ``bias[j] = 127 * sum_i W_q[i,j]``."""
-    weight = np.asarray(weight)
-    nmax = max(abs(weight.max()), abs(weight.min()))
-    scale = nmax / 127.0
-    wq = np.round(weight / scale)
+    ``bias[j] = 127 * sum_i W_q[i,j]``.
+
+    Promotion pinned to the numpy-1.x rules the reference ran under:
+    ``nmax`` is an fp32 scalar, ``nmax / 127.`` is a float64 scalar, and
+    ``tensor_value / scale`` (fp32 array / float64 scalar) is evaluated in fp32
+    with ``scale`` cast to fp32 -- which is also the value the op receives,
+    because the ``scale`` attr is a 32-bit float (octbit_ops_reg.cc:12)."""
+    weight = np.asarray(weight, dtype=np.float32)
+    nmax = max(abs(np.float32(weight.max())), abs(np.float32(weight.min())))
+    scale = float(nmax) / 127.0
+    wq = np.round((weight / np.float32(scale)).astype(np.float32))
     bias = (wq.astype(np.float64) * 127.0).sum(axis=0)
     return np.ascontiguousarray(wq.T).astype(np.int8), float(scale), bias
 

@@ -175,6 +175,8 @@ int kws_stream_step_host(kws_stream* st, const int16_t* pcm_host, int32_t chunk_
 int32_t kws_stream_max_frames(const kws_stream* st);
 /* Device pointer to the carried GRU state [layers, S, H] (for inspection). */
 const float* kws_stream_state(const kws_stream* st);
+/* Stream-ordered copy of the carried GRU state into state_out [layers, S, H]. */
+int kws_stream_copy_state(kws_stream* st, float* state_out, void* stream);
 /* Window decode of every stream as of the last step (labels as kws_ctc_decode). */
 int kws_stream_labels(kws_stream* st, int32_t* labels_out, int32_t max_labels,
                       int32_t* counts_out, void* stream);

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "kws_stream_step_host": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "kws_stream_max_frames": (c_int32, [c_void_p]),
     "kws_stream_state": (c_void_p, [c_void_p]),
+    "kws_stream_copy_state": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kws_stream_labels": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "kws_octbit_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "kws_octbit_matmul": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int64, c_int64,

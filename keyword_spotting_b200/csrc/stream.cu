@@ -311,6 +311,16 @@ extern "C" int kws_stream_reset(kws_stream* st, void* stream) {
 extern "C" int32_t kws_stream_max_frames(const kws_stream* st) { return st ? st->max_frames : 0; }
 extern "C" const float* kws_stream_state(const kws_stream* st) { return st ? st->state : nullptr; }
 
+extern "C" int kws_stream_copy_state(kws_stream* st, float* state_out, void* stream) {
+  clear_error();
+  KWS_REQUIRE(st != nullptr && state_out != nullptr, "NULL argument");
+  KWS_CUDA_OK(cudaSetDevice(st->model->device));
+  KWS_CUDA_OK(cudaMemcpyAsync(state_out, st->state,
+                              sizeof(float) * st->S * st->model->cfg.num_layers * kHidden,
+                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return KWS_OK;
+}
+
 extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk_len, int64_t ld_pcm,
                                int32_t* trigger_out, float* probs_out, int32_t* nframes_out, void* stream) {
   clear_error();

@@ -98,14 +98,9 @@ class StreamingDetector:
     def state(self) -> torch.Tensor:
         """Copy of the carried GRU state ``[layers, S, H]`` (CUDA tensor)."""
         cfg = self.model.config
-        n = cfg.num_layers * self.n_streams * cfg.hidden_size
         out = torch.empty((cfg.num_layers, self.n_streams, cfg.hidden_size), dtype=torch.float32, device=self.device)
-        src = self._lib.kws_stream_state(self._handle)
-        torch.cuda.current_stream(self.device).synchronize()
-        cudart = torch.cuda.cudart()
-        rc = cudart.cudaMemcpy(out.data_ptr(), src, n * 4, 3)     # cudaMemcpyDeviceToDevice
-        if int(rc[0] if isinstance(rc, tuple) else rc) != 0:
-            raise _lib.KwsCudaError("cudaMemcpy of the stream state failed")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.kws_stream_copy_state(self._handle, _tensors.ptr(out), _tensors.stream_ptr(self.device)))
         return out
 
     def window_labels(self, max_labels=None):

@@ -127,8 +127,14 @@ def test_octbit_cuda_tensors_and_quantised_model_weights():
         got = _oct(xd, torch.from_numpy(wq_t).cuda(), torch.from_numpy(bias).cuda(), scale)
         assert got.is_cuda
         assert got.cpu().numpy().tobytes() == want.tobytes()
-        # and the quantised product tracks the fp32 matmul (sanity of the whole recipe)
-        assert np.abs(got.cpu().numpy() - x @ W).max() < 0.05 * np.abs(x @ W).max() + 0.05
+        # and, where no adjacent pair saturates int16 (the reference's maddubs clips those),
+        # the quantised product tracks the fp32 matmul -- sanity of the whole recipe
+        q, _, _ = ooct.quantize_activations(x)
+        pair = (q.astype(np.int32)[:, None, :] * owq.astype(np.int32)[None]).reshape(A, owq.shape[0], -1, 2).sum(-1)
+        clean = (np.abs(pair) <= 32767).all(axis=2)
+        ref = x @ W
+        assert clean.any()
+        assert np.abs(got.cpu().numpy() - ref)[clean].max() < 0.03 * np.abs(ref).max() + 0.03
 
 
 def test_octbit_errors_follow_the_op():

@@ -79,9 +79,20 @@ typedef struct kws_model_weights {
   const float* fc_b;
 } kws_model_weights;
 
+/* Arithmetic of the recurrent kernel (K2+K3).
+ *   KWS_PRECISION_TC_FP16 (default): tcgen05 tensor cores, fp16 operands, fp32 accumulation and state --
+ *     the "fp32-accumulate mode" of the contract (softmax / state within 1e-3 of the fp32 graph).
+ *   KWS_PRECISION_FP32: every product in fp32 on the CUDA cores -- the accuracy baseline (~1e-5).        */
+typedef enum kws_precision {
+  KWS_PRECISION_FP32 = 0,
+  KWS_PRECISION_TC_FP16 = 1
+} kws_precision;
+
 int kws_model_create(const kws_model_config* cfg, const kws_model_weights* host_weights,
                      int device, kws_model** out);
 int kws_model_destroy(kws_model* m);
+int kws_model_set_precision(kws_model* m, int precision);
+int kws_model_get_precision(const kws_model* m);
 
 /* utils/stft.py:60-61: 1 + floor((L - fft)/hop); <= 0 when L < fft. */
 int kws_num_frames(const kws_model* m, int64_t signal_length);
@@ -215,6 +226,14 @@ int kws_octize_weight(const float* weight, int64_t in_dim, int64_t out_dim, int8
  * reference (:45).                                                           */
 int kws_positional_encoding(int32_t max_position, int32_t encoding_size, float* out,
                             void* stream);
+
+/* ----------------------------------------------------------------- self-test
+ * One 128 x N x K tensor-core product through the tcgen05 conventions the recurrent kernel builds on
+ * (A in TMEM when ss_mode == 0, in shared memory when 1; B in shared memory; fp32 accumulate in TMEM).
+ * A [128, K] fp32 DEVICE, B [N, K] fp32 HOST, D [128, N] fp32 DEVICE.  Both operands are rounded to fp16.
+ * Synchronises `stream`.                                                                       */
+int kws_debug_tc_gemm(const float* A, const float* B_host, float* D, int N, int K, int ss_mode,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,9 @@ KWS_ERR_UNSUPPORTED = -4
 PCM_F32 = 0
 PCM_I16 = 1
 
+PRECISION_FP32 = 0
+PRECISION_TC_FP16 = 1
+
 DECODE_CTC = 0
 DECODE_CTC2 = 1
 DECODE_STRICT = 2
@@ -56,6 +59,8 @@ _SIGNATURES = {
     "kws_device_count": (c_int, []),
     "kws_model_create": (c_int, [POINTER(ModelConfig), POINTER(ModelWeights), c_int, POINTER(c_void_p)]),
     "kws_model_destroy": (c_int, [c_void_p]),
+    "kws_model_set_precision": (c_int, [c_void_p, c_int]),
+    "kws_model_get_precision": (c_int, [c_void_p]),
     "kws_num_frames": (c_int, [c_void_p, c_int64]),
     "kws_model_reserve": (c_int, [c_void_p, c_int64, c_int32]),
     "kws_frontend_mel": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
@@ -81,6 +86,7 @@ _SIGNATURES = {
                                         c_void_p, c_void_p, c_size_t, c_void_p]),
     "kws_octize_weight": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
     "kws_positional_encoding": (c_int, [c_int32, c_int32, c_void_p, c_void_p]),
+    "kws_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

@@ -3,6 +3,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace kws {
@@ -52,6 +54,8 @@ static int upload(T** dst, const T* host, size_t n) {
   return KWS_OK;
 }
 
+void pack_tc_weights(const float* gates_kernel, const float* cand_kernel, int in_dim, std::vector<__half>* out, int* kx_out);
+
 static void free_model(kws_model* m) {
   if (!m) return;
   cudaFree(m->mel_basis);
@@ -65,6 +69,8 @@ static void free_model(kws_model* m) {
     cudaFree(m->layer[l].gates_bias);
     cudaFree(m->layer[l].cand_kernel);
     cudaFree(m->layer[l].cand_bias);
+    cudaFree(m->layer[l].tc_wpack);
+    cudaFree(m->layer[l].tc_bias);
   }
   cudaFree(m->fc_w);
   cudaFree(m->fc_b);
@@ -153,6 +159,17 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
     if (rc == KWS_OK) rc = upload(&m->layer[l].gates_bias, w->gates_bias[l], 2 * H);
     if (rc == KWS_OK) rc = upload(&m->layer[l].cand_kernel, w->cand_kernel[l], static_cast<size_t>(in + H) * H);
     if (rc == KWS_OK) rc = upload(&m->layer[l].cand_bias, w->cand_bias[l], H);
+    if (rc == KWS_OK) {
+      std::vector<__half> packed;
+      pack_tc_weights(w->gates_kernel[l], w->cand_kernel[l], in, &packed, &m->layer[l].tc_kx);
+      __half* dptr = nullptr;
+      rc = upload(&dptr, packed.data(), packed.size());
+      m->layer[l].tc_wpack = dptr;
+      std::vector<float> fused(3 * H);
+      for (int i = 0; i < 2 * H; ++i) fused[i] = w->gates_bias[l][i];
+      for (int i = 0; i < H; ++i) fused[2 * H + i] = w->cand_bias[l][i];
+      if (rc == KWS_OK) rc = upload(&m->layer[l].tc_bias, fused.data(), fused.size());
+    }
   }
   if (rc == KWS_OK) rc = upload(&m->fc_w, w->fc_w, static_cast<size_t>(H) * C);
   if (rc == KWS_OK) rc = upload(&m->fc_b, w->fc_b, C);
@@ -172,6 +189,22 @@ extern "C" int kws_model_destroy(kws_model* m) {
   }
   return KWS_OK;
 }
+
+extern "C" int kws_model_set_precision(kws_model* m, int precision) {
+  clear_error();
+  KWS_REQUIRE(m != nullptr, "model is NULL");
+  KWS_REQUIRE(precision == KWS_PRECISION_FP32 || precision == KWS_PRECISION_TC_FP16, "unknown precision %d", precision);
+  m->precision = precision;
+  return KWS_OK;
+}
+
+extern "C" int kws_model_get_precision(const kws_model* m) { return m ? m->precision : -1; }
+
+namespace kws {
+int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st) {
+  return m->precision == KWS_PRECISION_FP32 ? launch_gru_fp32(m, a, st) : launch_gru_tc(m, a, st);
+}
+}  // namespace kws
 
 extern "C" int kws_num_frames(const kws_model* m, int64_t L) {
   const int fft = m ? m->cfg.fft_size : kFft, hop = m ? m->cfg.hop_size : kHop;

@@ -56,6 +56,10 @@ struct LayerWeights {
   float* gates_bias = nullptr;    // [2H]
   float* cand_kernel = nullptr;   // [in+H, H]
   float* cand_bias = nullptr;     // [H]
+  // tensor-core path (gru_tc.cu): fp16 B operand [384, tc_kx+H] in the canonical smem layout, fused bias [384]
+  int tc_kx = 0;
+  void* tc_wpack = nullptr;
+  float* tc_bias = nullptr;
 };
 
 struct MelSparse {               // per-band non-zero bin range of the mel basis
@@ -72,6 +76,7 @@ struct MelSparse {               // per-band non-zero bin range of the mel basis
 struct kws_model {
   kws_model_config cfg;
   int device = 0;
+  int precision = KWS_PRECISION_TC_FP16;
   float* mel_basis = nullptr;     // [201, M] dense, as given
   kws::MelSparse mel;
   float2* twiddle400 = nullptr;   // [400] exp(-2*pi*i*k/400)
@@ -113,6 +118,8 @@ struct GruArgs {
   float* probs = nullptr;                 // [S, n, C]
   float* logits = nullptr;                // [S, n, C] or null
 };
-int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st);
+int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st);        // dispatches on m->precision
+int launch_gru_fp32(kws_model* m, const GruArgs& a, cudaStream_t st);   // gru.cu   (exact fp32 FFMA)
+int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st);     // gru_tc.cu (tcgen05, fp16 operands)
 
 }  // namespace kws

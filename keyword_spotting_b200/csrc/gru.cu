@@ -307,7 +307,7 @@ static size_t gru_smem_bytes(int in_dim) {
                           kH * kMaxClasses + kMaxClasses + kTs * kMaxClasses);
 }
 
-int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st) {
+int launch_gru_fp32(kws_model* m, const GruArgs& a, cudaStream_t st) {
   if (a.S <= 0) return KWS_OK;
   const int L = m->cfg.num_layers;
   const long ntiles = ceil_div(a.S, kTs);

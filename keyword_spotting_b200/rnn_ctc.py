@@ -102,7 +102,10 @@ class ModelWeights:
 class DeployModel:
     """models/rnn_ctc.py:113-166 on a B200.  Owns a ``kws_model`` handle."""
 
-    def __init__(self, config: Optional[Config] = None, weights: Optional[ModelWeights] = None, device=None):
+    def __init__(self, config: Optional[Config] = None, weights: Optional[ModelWeights] = None, device=None,
+                 precision: str = "tc"):
+        """``precision``: ``"tc"`` (default) = tcgen05 tensor cores, fp16 operands / fp32 accumulate and state;
+        ``"fp32"`` = every product in fp32 on the CUDA cores (the accuracy baseline)."""
         self.config = config or Config()
         self.device = _tensors.require_cuda(device)
         self.weights = weights if weights is not None else ModelWeights.random_init(self.config)
@@ -128,6 +131,14 @@ class DeployModel:
         _lib.check(self._lib.kws_model_create(ctypes.byref(cfg), ctypes.byref(cw), self.device.index,
                                               ctypes.byref(handle)))
         self._handle = handle
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str):
+        modes = {"tc": _lib.PRECISION_TC_FP16, "fp32": _lib.PRECISION_FP32}
+        if precision not in modes:
+            raise _lib.InvalidArgumentError("precision must be 'tc' or 'fp32'")
+        _lib.check(self._lib.kws_model_set_precision(self._handle, modes[precision]))
+        self.precision = precision
 
     # -- lifetime
     def close(self):

@@ -186,23 +186,31 @@ def _sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 
 
-def gru_cell(x, h, gates_kernel, gates_bias, cand_kernel, cand_bias, dtype=np.float32):
+def _operand(a, operand_dtype, dtype):
+    """Model of a reduced-precision matmul OPERAND (accumulation stays in ``dtype``): used to emulate the
+    tensor-core path's arithmetic (fp16 operands, fp32 accumulate) so the kernel's logic can be checked far
+    below the 1e-3 contract tolerance.  ``None`` = the reference's plain fp32 graph."""
+    return a if operand_dtype is None else a.astype(operand_dtype).astype(dtype)
+
+
+def gru_cell(x, h, gates_kernel, gates_bias, cand_kernel, cand_bias, dtype=np.float32, operand_dtype=None):
     """One TF GRUCell step.  NOTE reset gate is applied to h BEFORE the
     candidate matmul (not the cuDNN / torch.nn.GRU formulation)."""
     one = dtype(1.0)
-    xh = np.concatenate([x, h], axis=1)
-    gate_in = (np.matmul(xh, gates_kernel.astype(dtype)) + gates_bias.astype(dtype)).astype(dtype)
+    od = operand_dtype
+    xh = _operand(np.concatenate([x, h], axis=1), od, dtype)
+    gate_in = (np.matmul(xh, _operand(gates_kernel.astype(dtype), od, dtype)) + gates_bias.astype(dtype)).astype(dtype)
     gates = _sigmoid(gate_in).astype(dtype)
     H = h.shape[1]
     r, u = gates[:, :H], gates[:, H:]
-    xrh = np.concatenate([x, (r * h).astype(dtype)], axis=1)
-    cand = (np.matmul(xrh, cand_kernel.astype(dtype)) + cand_bias.astype(dtype)).astype(dtype)
+    xrh = _operand(np.concatenate([x, (r * h).astype(dtype)], axis=1), od, dtype)
+    cand = (np.matmul(xrh, _operand(cand_kernel.astype(dtype), od, dtype)) + cand_bias.astype(dtype)).astype(dtype)
     c = np.tanh(cand).astype(dtype)
     return (u * h + (one - u) * c).astype(dtype)
 
 
 def gru_forward(x: np.ndarray, state: np.ndarray, w: Weights,
-                seq_len: Optional[np.ndarray] = None, dtype=np.float32
+                seq_len: Optional[np.ndarray] = None, dtype=np.float32, operand_dtype=None
                 ) -> Tuple[np.ndarray, np.ndarray]:
     """``inference1`` (models/rnn_ctc.py:202-244).
 
@@ -220,7 +228,7 @@ def gru_forward(x: np.ndarray, state: np.ndarray, w: Weights,
         live = None if seq_len is None else (t < np.asarray(seq_len))[:, None]
         for l in range(w.num_layers):
             new_h = gru_cell(inp, h[l], w.gates_kernel[l], w.gates_bias[l],
-                             w.cand_kernel[l], w.cand_bias[l], dtype)
+                             w.cand_kernel[l], w.cand_bias[l], dtype, operand_dtype)
             if live is not None:
                 new_h = np.where(live, new_h, h[l])
             h[l] = new_h
@@ -246,15 +254,15 @@ def softmax(logits: np.ndarray, dtype=np.float32) -> np.ndarray:
     return (e / e.sum(axis=-1, keepdims=True)).astype(dtype)
 
 
-def mel_forward(mel: np.ndarray, state: np.ndarray, w: Weights, seq_len=None, dtype=np.float32):
+def mel_forward(mel: np.ndarray, state: np.ndarray, w: Weights, seq_len=None, dtype=np.float32, operand_dtype=None):
     """(mel frames, rnn_state) -> (softmax, rnn_state, logits); the commented
     mel-input form of the deployment graph (models/rnn_ctc.py:150-153)."""
-    out, new_state = gru_forward(mel, state, w, seq_len, dtype)
+    out, new_state = gru_forward(mel, state, w, seq_len, dtype, operand_dtype)
     logits = fc_logits(out, w, dtype)
     return softmax(logits, dtype), new_state, logits
 
 
-def deploy_forward(pcm: np.ndarray, state: np.ndarray, w: Weights, dtype=np.float32):
+def deploy_forward(pcm: np.ndarray, state: np.ndarray, w: Weights, dtype=np.float32, operand_dtype=None):
     """``DeployModel`` (models/rnn_ctc.py:113-166) batched over streams.
 
     pcm ``[S, L]`` float (or ``[L]``, the reference's batch-1 form), state
@@ -264,7 +272,7 @@ def deploy_forward(pcm: np.ndarray, state: np.ndarray, w: Weights, dtype=np.floa
     if pcm.ndim == 1:
         pcm = pcm[None, :]
     mel = pcm_to_mel(pcm.astype(dtype), w, dtype)
-    return mel_forward(mel, state, w, None, dtype)
+    return mel_forward(mel, state, w, None, dtype, operand_dtype)
 
 
 def pcm16_to_float(x: np.ndarray) -> np.ndarray:

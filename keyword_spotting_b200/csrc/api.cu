@@ -147,10 +147,11 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
   if (rc == KWS_OK) rc = upload(&m->mel.offset, offset.data(), offset.size());
   if (rc == KWS_OK) rc = upload(&m->mel.weight, packed.data(), packed.size());
   std::vector<float2> tw(kFft);
-  for (int i = 0; i < kFft; ++i) {
-    const double a = -2.0 * M_PI * static_cast<double>(i) / kFft;
-    tw[i] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
-  }
+  for (int n1 = 0; n1 < 20; ++n1)
+    for (int k2 = 0; k2 < 20; ++k2) {     // k2-major table of W400^(n1*k2), fft400.cuh twt_index
+      const double a = -2.0 * M_PI * static_cast<double>(n1 * k2) / kFft;
+      tw[k2 * 20 + n1] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+    }
   if (rc == KWS_OK) rc = upload(&m->twiddle400, tw.data(), tw.size());
   for (int l = 0; l < cfg->num_layers && rc == KWS_OK; ++l) {
     const int in = l == 0 ? M : H;

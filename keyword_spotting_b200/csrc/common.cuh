@@ -79,7 +79,7 @@ struct kws_model {
   int precision = KWS_PRECISION_TC_FP16;
   float* mel_basis = nullptr;     // [201, M] dense, as given
   kws::MelSparse mel;
-  float2* twiddle400 = nullptr;   // [400] exp(-2*pi*i*k/400)
+  float2* twiddle400 = nullptr;   // [400] k2-major: [k2*20+n1] = exp(-2*pi*i*n1*k2/400)  (fft400.cuh)
   kws::LayerWeights layer[kws::kMaxLayers];
   float* fc_w = nullptr;          // [H, C]
   float* fc_b = nullptr;          // [C]
@@ -104,8 +104,20 @@ struct PcmSource {
   const int32_t* head_len = nullptr;  // [S] or null (= 0)
 };
 
+// The streaming server's per-chunk pre-step, fused into the front end when the chunk fits one work item
+// (frontend_can_fuse_pre): VAD flag, frame count and next carried tail are produced by the same CTA that
+// stages the chunk, so the PCM is read once.
+struct FrontendPre {
+  long long vad_limit = 0;            // speech iff sum|x_i16| > vad_limit
+  int16_t* tail_next = nullptr;       // [S, 400]
+  int32_t* len_next = nullptr;        // [S]
+  unsigned char* silence = nullptr;   // [S]
+  int32_t* nframes_out = nullptr;     // [S]
+};
+bool frontend_can_fuse_pre(int chunk_len, int tail_cap);
 int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t max_frames,
-                    const int32_t* nframes /*[S] or null*/, float* mel_out, cudaStream_t st);
+                    const int32_t* nframes /*[S] or null*/, float* mel_out, cudaStream_t st,
+                    const FrontendPre* pre = nullptr);
 
 struct GruArgs {
   const float* x = nullptr;       // layer-0 input [S, n, M] row-major

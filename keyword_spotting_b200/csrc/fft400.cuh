@@ -1,4 +1,4 @@
-// 400-point DFT of two real frames at once, split over 10 cooperating threads.
+// 400-point DFT of two real frames at once, one DFT-20 column per thread, 20 threads per frame pair.
 //
 // Replaces tf.abs(tf.spectral.rfft(frames, [400])) (models/rnn_ctc.py:137) for
 // rectangular-window frames (utils/stft.py:27-81).
@@ -11,12 +11,15 @@
 //   twiddle: Y'[n1][k2] = Y[n1][k2] * W400^(n1*k2)
 //   stage 2: Z[20*k1+k2] = sum_n1 Y'[n1][k2] * W20^(n1*k1)        (DFT-20 per k2)
 // Each DFT-20 is a twiddle-free Good-Thomas 4 x 5 prime-factor transform held in
-// registers.  Thread j of the 10 owns n1 in {j, j+10} in stage 1 and k2 in
-// {j, j+10} in stage 2; the exchange goes through a [20][21]-slot complex buffer
-// (row stride padded to 21 to keep the 64-bit accesses on distinct banks).
+// registers.  Thread c of the pair's 20 owns column n1 = c in stage 1 and column
+// k2 = c in stage 2; the single exchange goes through a [20][21]-slot complex buffer
+// (row stride 21: a half-warp's 64-bit accesses land on 16 distinct bank pairs in both
+// directions).  The thread that ends stage 2 with Z[20*k1+k2] in registers untangles its
+// own bins k <= 200 and only needs Z[400-k] from its mirror column, so stage 2 publishes
+// just rows 10..19; rows 0..9 of the buffer are then reused for the 2 x 201 magnitudes.
 //
 // Everything here is __host__ __device__ so the index logic is unit-tested on the
-// CPU (tests/test_fft400_host.py builds tests/fft400_host.cpp with g++).
+// CPU (tests/test_host.py builds tests/host/fft400_host.cpp with g++).
 #pragma once
 
 #if defined(__CUDACC__)
@@ -33,11 +36,12 @@ struct alignas(8) cpx {
 };
 
 constexpr int kN = 400;
-constexpr int kR = 20;            // 400 = kR * kR
+constexpr int kR = 20;            // 400 = kR * kR; also the threads cooperating on one frame pair
 constexpr int kRowStride = 21;    // padded slots per row of the exchange buffer
 constexpr int kBufSlots = kR * kRowStride;   // 420 complex slots
-constexpr int kThreads = 10;      // threads cooperating on one frame pair
 constexpr int kPairWindow = 560;  // samples spanned by two consecutive frames (160 + 400)
+constexpr int kBins = kN / 2 + 1; // 201
+constexpr int kMagB = kBins;      // magnitudes of frame b start here (floats, over buffer rows 0..9)
 
 KWS_HD cpx cadd(cpx a, cpx b) { return cpx{a.re + b.re, a.im + b.im}; }
 KWS_HD cpx csub(cpx a, cpx b) { return cpx{a.re - b.re, a.im - b.im}; }
@@ -86,65 +90,65 @@ KWS_HD void dft20_pfa(cpx (&v)[20]) {
          v[(5 * k1 + 16) % 20]);
 }
 
-KWS_HD constexpr int slot_of(int k) { return (k / kR) * kRowStride + (k % kR); }
+// Twiddle table layout used by stage 1: k2-major, twt[k2*20 + n1] = exp(-2*pi*i*n1*k2/400), so the 20
+// threads of a pair (consecutive n1) read consecutive slots for a fixed k2.
+KWS_HD constexpr int twt_index(int n1, int k2) { return k2 * kR + n1; }
 
-// stage 1 + twiddle for thread j: columns n1 = j, j+10 of the pair window.
-//   win  : this pair's samples; frame a = win[0..399], frame b = win[160..559]
-//   tw   : tw[m] = exp(-2*pi*i*m/400), m < 400
-//   buf  : exchange buffer, Y'[n1][k2] -> buf[n1*21 + k2]
-KWS_HD void stage1(int j, const float* win, const cpx* tw, cpx* buf) {
+// stage 1 + twiddle for column n1.  v[n2] = a[n1+20*n2] + i*b[n1+20*n2] on entry (filled by the caller).
+//   buf : exchange buffer, Y'[n1][k2] -> buf[n1*21 + k2]
+KWS_HD void stage1_col(int n1, cpx (&v)[20], const cpx* twt, cpx* buf) {
+  dft20_pfa(v);
+  buf[n1 * kRowStride] = v[pfa_slot(0)];                                // W^0 = 1
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const int n1 = j + 10 * c;
-    cpx v[20];
-#pragma unroll
-    for (int n2 = 0; n2 < 20; ++n2) {
-      v[n2].re = win[n1 + 20 * n2];
-      v[n2].im = win[160 + n1 + 20 * n2];
-    }
-    dft20_pfa(v);
-#pragma unroll
-    for (int k2 = 0; k2 < 20; ++k2) buf[n1 * kRowStride + k2] = cmul(v[pfa_slot(k2)], tw[n1 * k2]);
-  }
+  for (int k2 = 1; k2 < kR; ++k2) buf[n1 * kRowStride + k2] = cmul(v[pfa_slot(k2)], twt[twt_index(n1, k2)]);
 }
 
-// stage 2 for thread j: columns k2 = j, j+10; in place (a thread only touches its own columns)
-KWS_HD void stage2(int j, cpx* buf) {
+// stage 2 for column k2 (after a barrier).  On return Z[20*k1 + k2] == v[pfa_slot(k1)]; rows 10..19 of the
+// column are written back in place (a column is only ever touched by its owner until the next barrier).
+KWS_HD void stage2_col(int k2, cpx* buf, cpx (&v)[20]) {
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const int k2 = j + 10 * c;
-    cpx v[20];
+  for (int n1 = 0; n1 < kR; ++n1) v[n1] = buf[n1 * kRowStride + k2];
+  dft20_pfa(v);
 #pragma unroll
-    for (int n1 = 0; n1 < 20; ++n1) v[n1] = buf[n1 * kRowStride + k2];
-    dft20_pfa(v);
-#pragma unroll
-    for (int k1 = 0; k1 < 20; ++k1) buf[k1 * kRowStride + k2] = v[pfa_slot(k1)];   // Z[20*k1 + k2]
-  }
+  for (int k1 = kR / 2; k1 < kR; ++k1) buf[k1 * kRowStride + k2] = v[pfa_slot(k1)];
 }
 
-// |A[k]| and |B[k]| for the bins k = j, j+10, ... <= 200 owned by thread j.
-// mag_a / mag_b get up to 21 values each (index i <-> bin j + 10*i).
-KWS_HD int untangle(int j, const cpx* buf, float (&mag_a)[21], float (&mag_b)[21]) {
-  int cnt = 0;
-#pragma unroll
-  for (int i = 0; i < 21; ++i) {
-    const int k = j + 10 * i;
-    if (k <= 200) {
-      const cpx zk = buf[slot_of(k)];
-      const cpx zm = buf[slot_of((kN - k) % kN)];
-      const float ar = zk.re + zm.re, ai = zk.im - zm.im;   // 2*A[k]
-      const float br = zk.re - zm.re, bi = zk.im + zm.im;   // 2i*B[k] rotated: same modulus
+KWS_HD float mag_of(float re, float im, float scale) {
 #if defined(__CUDA_ARCH__)
-      mag_a[i] = 0.5f * sqrtf(ar * ar + ai * ai);
-      mag_b[i] = 0.5f * sqrtf(br * br + bi * bi);
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(re * re + im * im));
+  return scale * r;
 #else
-      mag_a[i] = 0.5f * __builtin_sqrtf(ar * ar + ai * ai);
-      mag_b[i] = 0.5f * __builtin_sqrtf(br * br + bi * bi);
+  return scale * __builtin_sqrtf(re * re + im * im);
 #endif
-      cnt = i + 1;
-    }
+}
+
+// |A[k]|, |B[k]| for the bins k = 20*k1 + k2 <= 200 of column k2 (after a barrier).  `v` is the register
+// state left by stage2_col.  Results go to mag[k] (frame a) and mag[kMagB + k] (frame b), where `mag` is the
+// float view of the SAME buffer's rows 0..9 -- nobody reads those rows any more.  `scale` = 1/2 times the
+// sample scale (the DFT is linear, so int16 samples are transformed unscaled and 2^-15 is applied here).
+KWS_HD void untangle_col(int k2, const cpx (&v)[20], const cpx* buf, float scale, float* mag) {
+  const int mcol = k2 == 0 ? 0 : kR - k2;          // column of Z[400 - k]
+  const int mrow0 = k2 == 0 ? kR : kR - 1;         // its row is mrow0 - k1
+#pragma unroll
+  for (int k1 = 0; k1 < kR / 2; ++k1) {
+    const int k = kR * k1 + k2;
+    const cpx zk = v[pfa_slot(k1)];
+    int mrow = mrow0 - k1;
+    const bool self = mrow == kR;                   // k == 0: Z[400] = Z[0] = zk
+    if (self) mrow = kR - 1;                        // any published slot; the value is discarded
+    cpx zm = buf[mrow * kRowStride + mcol];
+    if (self) zm = zk;
+    const float ar = zk.re + zm.re, ai = zk.im - zm.im;   // 2*A[k]
+    const float br = zk.re - zm.re, bi = zk.im + zm.im;   // 2i*B[k] rotated: same modulus
+    mag[k] = mag_of(ar, ai, scale);
+    mag[kMagB + k] = mag_of(br, bi, scale);
   }
-  return cnt;
+  if (k2 == 0) {                                    // k = 200 = 400 - 200: its own mirror
+    const cpx z = v[pfa_slot(kR / 2)];
+    mag[kN / 2] = mag_of(2.0f * z.re, 0.0f, scale);
+    mag[kMagB + kN / 2] = mag_of(0.0f, 2.0f * z.im, scale);
+  }
 }
 
 }  // namespace fft

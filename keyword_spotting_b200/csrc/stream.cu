@@ -338,22 +338,38 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
   const int C = m->cfg.num_classes;
 
   const long long vad_limit = static_cast<long long>(st->cfg.vad_threshold) * 32768LL;
-  stream_pre_kernel<<<static_cast<unsigned>(ceil_div(S * 32, 256)), 256, 0, cs>>>(
-      pcm, ld_pcm, chunk_len, S, vad_limit, st->tail[cur], st->tail_len[cur], st->tail[nxt], st->tail_len[nxt],
-      st->silence, st->nframes, n_step);
-  KWS_LAUNCH_OK("stream_pre_kernel");
+  PcmSource src;
+  src.body = pcm;
+  src.ld_body = ld_pcm;
+  src.body_len = chunk_len;
+  src.body_dtype = KWS_PCM_I16;
+  src.head = st->tail[cur];
+  src.ld_head = kTailCap;
+  src.head_len = st->tail_len[cur];
+  const bool fused = frontend_can_fuse_pre(chunk_len, kTailCap);
+  if (fused) {
+    // one pass over the chunk: VAD + tail carry + frame count + framing/FFT/mel
+    FrontendPre pre;
+    pre.vad_limit = vad_limit;
+    pre.tail_next = st->tail[nxt];
+    pre.len_next = st->tail_len[nxt];
+    pre.silence = st->silence;
+    pre.nframes_out = st->nframes;
+    int rc = launch_frontend(m, src, S, n_step, nullptr, st->mel, cs, &pre);
+    if (rc != KWS_OK) return rc;
+  } else {
+    stream_pre_kernel<<<static_cast<unsigned>(ceil_div(S * 32, 256)), 256, 0, cs>>>(
+        pcm, ld_pcm, chunk_len, S, vad_limit, st->tail[cur], st->tail_len[cur], st->tail[nxt], st->tail_len[nxt],
+        st->silence, st->nframes, n_step);
+    KWS_LAUNCH_OK("stream_pre_kernel");
+  }
 
   if (n_step > 0) {
-    PcmSource src;
-    src.body = pcm;
-    src.ld_body = ld_pcm;
-    src.body_len = chunk_len;
-    src.body_dtype = KWS_PCM_I16;
-    src.head = st->tail[cur];
-    src.ld_head = kTailCap;
-    src.head_len = st->tail_len[cur];
-    int rc = launch_frontend(m, src, S, n_step, st->nframes, st->mel, cs);
-    if (rc != KWS_OK) return rc;
+    if (!fused) {
+      int rc = launch_frontend(m, src, S, n_step, st->nframes, st->mel, cs);
+      if (rc != KWS_OK) return rc;
+    }
+    int rc = KWS_OK;
     GruArgs a;
     a.x = st->mel;
     a.S = S;

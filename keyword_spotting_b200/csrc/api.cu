@@ -54,7 +54,8 @@ static int upload(T** dst, const T* host, size_t n) {
   return KWS_OK;
 }
 
-void pack_tc_weights(const float* gates_kernel, const float* cand_kernel, int in_dim, std::vector<__half>* out, int* kx_out);
+void pack_tc_weights(const float* gates_kernel, const float* cand_kernel, int in_dim, bool split, std::vector<__half>* out,
+                     int* kx_out, int* kxw_out);
 
 static void free_model(kws_model* m) {
   if (!m) return;
@@ -146,11 +147,11 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
   if (rc == KWS_OK) rc = upload(&m->mel.count, count.data(), count.size());
   if (rc == KWS_OK) rc = upload(&m->mel.offset, offset.data(), offset.size());
   if (rc == KWS_OK) rc = upload(&m->mel.weight, packed.data(), packed.size());
-  std::vector<float2> tw(kFft);
-  for (int n1 = 0; n1 < 20; ++n1)
-    for (int k2 = 0; k2 < 20; ++k2) {     // k2-major table of W400^(n1*k2), fft400.cuh twt_index
-      const double a = -2.0 * M_PI * static_cast<double>(n1 * k2) / kFft;
-      tw[k2 * 20 + n1] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+  std::vector<float2> tw(20 * 52);          // periodic k2-major table of W400^(n1*k2) (fft400.cuh: kTwStride = 52)
+  for (int k2 = 0; k2 < 20; ++k2)
+    for (int j = 0; j < 52; ++j) {
+      const double a = -2.0 * M_PI * static_cast<double>((j % 20) * k2) / kFft;
+      tw[k2 * 52 + j] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
     }
   if (rc == KWS_OK) rc = upload(&m->twiddle400, tw.data(), tw.size());
   for (int l = 0; l < cfg->num_layers && rc == KWS_OK; ++l) {
@@ -162,7 +163,8 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
     if (rc == KWS_OK) rc = upload(&m->layer[l].cand_bias, w->cand_bias[l], H);
     if (rc == KWS_OK) {
       std::vector<__half> packed;
-      pack_tc_weights(w->gates_kernel[l], w->cand_kernel[l], in, &packed, &m->layer[l].tc_kx);
+      pack_tc_weights(w->gates_kernel[l], w->cand_kernel[l], in, /*split=*/l == 0 && in <= 64, &packed, &m->layer[l].tc_kx,
+                      &m->layer[l].tc_kxw);
       __half* dptr = nullptr;
       rc = upload(&dptr, packed.data(), packed.size());
       m->layer[l].tc_wpack = dptr;

@@ -57,7 +57,8 @@ struct LayerWeights {
   float* cand_kernel = nullptr;   // [in+H, H]
   float* cand_bias = nullptr;     // [H]
   // tensor-core path (gru_tc.cu): fp16 B operand [384, tc_kx+H] in the canonical smem layout, fused bias [384]
-  int tc_kx = 0;
+  int tc_kx = 0;                // x width padded to 16
+  int tc_kxw = 0;               // x columns in tc_wpack (2*tc_kx for layer 0: hi and lo parts)
   void* tc_wpack = nullptr;
   float* tc_bias = nullptr;
 };
@@ -79,7 +80,7 @@ struct kws_model {
   int precision = KWS_PRECISION_TC_FP16;
   float* mel_basis = nullptr;     // [201, M] dense, as given
   kws::MelSparse mel;
-  float2* twiddle400 = nullptr;   // [400] k2-major: [k2*20+n1] = exp(-2*pi*i*n1*k2/400)  (fft400.cuh)
+  float2* twiddle400 = nullptr;   // [20*52] periodic k2-major twiddles (fft400.cuh kTwStride)
   kws::LayerWeights layer[kws::kMaxLayers];
   float* fc_w = nullptr;          // [H, C]
   float* fc_b = nullptr;          // [C]

@@ -16,7 +16,7 @@
 // (row stride 21: a half-warp's 64-bit accesses land on 16 distinct bank pairs in both
 // directions).  The thread that ends stage 2 with Z[20*k1+k2] in registers untangles its
 // own bins k <= 200 and only needs Z[400-k] from its mirror column, so stage 2 publishes
-// just rows 10..19; rows 0..9 of the buffer are then reused for the 2 x 201 magnitudes.
+// just rows 10..19.
 //
 // Everything here is __host__ __device__ so the index logic is unit-tested on the
 // CPU (tests/test_host.py builds tests/host/fft400_host.cpp with g++).
@@ -41,7 +41,6 @@ constexpr int kRowStride = 21;    // padded slots per row of the exchange buffer
 constexpr int kBufSlots = kR * kRowStride;   // 420 complex slots
 constexpr int kPairWindow = 560;  // samples spanned by two consecutive frames (160 + 400)
 constexpr int kBins = kN / 2 + 1; // 201
-constexpr int kMagB = kBins;      // magnitudes of frame b start here (floats, over buffer rows 0..9)
 
 KWS_HD cpx cadd(cpx a, cpx b) { return cpx{a.re + b.re, a.im + b.im}; }
 KWS_HD cpx csub(cpx a, cpx b) { return cpx{a.re - b.re, a.im - b.im}; }
@@ -90,17 +89,22 @@ KWS_HD void dft20_pfa(cpx (&v)[20]) {
          v[(5 * k1 + 16) % 20]);
 }
 
-// Twiddle table layout used by stage 1: k2-major, twt[k2*20 + n1] = exp(-2*pi*i*n1*k2/400), so the 20
-// threads of a pair (consecutive n1) read consecutive slots for a fixed k2.
-KWS_HD constexpr int twt_index(int n1, int k2) { return k2 * kR + n1; }
+// Twiddle table used by stage 1: k2-major rows of kTwStride = 52 slots, periodically extended in n1:
+//   twp[k2*52 + j] = exp(-2*pi*i*(j % 20)*k2/400),  j < 52.
+// Thread t of a CTA owns column n1 = t % 20; with j = (12*warp) % 20 + lane (== n1 mod 20) the 32 lanes of a
+// warp -- which straddle two frame pairs -- read 32 CONSECUTIVE slots for a fixed k2, i.e. conflict-free.
+constexpr int kTwStride = 52;
+constexpr int kTwSlots = kR * kTwStride;       // 1040
+KWS_HD constexpr int tw_base(int warp, int lane) { return (12 * warp) % kR + lane; }
 
 // stage 1 + twiddle for column n1.  v[n2] = a[n1+20*n2] + i*b[n1+20*n2] on entry (filled by the caller).
+//   tw  : the table above, already offset by this thread's tw_base
 //   buf : exchange buffer, Y'[n1][k2] -> buf[n1*21 + k2]
-KWS_HD void stage1_col(int n1, cpx (&v)[20], const cpx* twt, cpx* buf) {
+KWS_HD void stage1_col(int n1, cpx (&v)[20], const cpx* tw, cpx* buf) {
   dft20_pfa(v);
   buf[n1 * kRowStride] = v[pfa_slot(0)];                                // W^0 = 1
 #pragma unroll
-  for (int k2 = 1; k2 < kR; ++k2) buf[n1 * kRowStride + k2] = cmul(v[pfa_slot(k2)], twt[twt_index(n1, k2)]);
+  for (int k2 = 1; k2 < kR; ++k2) buf[n1 * kRowStride + k2] = cmul(v[pfa_slot(k2)], tw[k2 * kTwStride]);
 }
 
 // stage 2 for column k2 (after a barrier).  On return Z[20*k1 + k2] == v[pfa_slot(k1)]; rows 10..19 of the
@@ -124,10 +128,12 @@ KWS_HD float mag_of(float re, float im, float scale) {
 }
 
 // |A[k]|, |B[k]| for the bins k = 20*k1 + k2 <= 200 of column k2 (after a barrier).  `v` is the register
-// state left by stage2_col.  Results go to mag[k] (frame a) and mag[kMagB + k] (frame b), where `mag` is the
-// float view of the SAME buffer's rows 0..9 -- nobody reads those rows any more.  `scale` = 1/2 times the
-// sample scale (the DFT is linear, so int16 samples are transformed unscaled and 2^-15 is applied here).
-KWS_HD void untangle_col(int k2, const cpx (&v)[20], const cpx* buf, float scale, float* mag) {
+// state left by stage2_col; Z[400-k] comes from the mirror column's published rows 10..19.  Results go to
+// mag_a[k*mag_stride] and mag_b[k*mag_stride] (any memory that nobody is reading during this phase).
+// `scale` = 1/2 times the sample scale (the DFT is linear, so int16 samples are transformed unscaled and 2^-15
+// is applied here).
+KWS_HD void untangle_col(int k2, const cpx (&v)[20], const cpx* buf, float scale, float* mag_a, float* mag_b,
+                         int mag_stride) {
   const int mcol = k2 == 0 ? 0 : kR - k2;          // column of Z[400 - k]
   const int mrow0 = k2 == 0 ? kR : kR - 1;         // its row is mrow0 - k1
 #pragma unroll
@@ -141,13 +147,13 @@ KWS_HD void untangle_col(int k2, const cpx (&v)[20], const cpx* buf, float scale
     if (self) zm = zk;
     const float ar = zk.re + zm.re, ai = zk.im - zm.im;   // 2*A[k]
     const float br = zk.re - zm.re, bi = zk.im + zm.im;   // 2i*B[k] rotated: same modulus
-    mag[k] = mag_of(ar, ai, scale);
-    mag[kMagB + k] = mag_of(br, bi, scale);
+    mag_a[k * mag_stride] = mag_of(ar, ai, scale);
+    mag_b[k * mag_stride] = mag_of(br, bi, scale);
   }
   if (k2 == 0) {                                    // k = 200 = 400 - 200: its own mirror
     const cpx z = v[pfa_slot(kR / 2)];
-    mag[kN / 2] = mag_of(2.0f * z.re, 0.0f, scale);
-    mag[kMagB + kN / 2] = mag_of(0.0f, 2.0f * z.im, scale);
+    mag_a[(kN / 2) * mag_stride] = mag_of(2.0f * z.re, 0.0f, scale);
+    mag_b[(kN / 2) * mag_stride] = mag_of(0.0f, 2.0f * z.im, scale);
   }
 }
 

@@ -14,9 +14,11 @@
 // (fft400.cuh).  The item's PCM (5360 samples) is staged once in shared memory as fp32 with coalesced 16-byte
 // loads; every 320-sample block is skewed by 20 floats so that the 32 lanes of a warp -- which straddle two
 // pairs -- read 32 distinct banks.  int16 samples are transformed unscaled (the DFT is linear) and 2^-15 is
-// folded into the magnitude.  The mel projection uses the per-band non-zero bin ranges of the basis found at
-// model creation, so it costs ~2*201 FMAs per frame for a triangular filterbank yet stays exact for any dense
-// basis.  Persistent grid: (resident CTAs per SM) x 148 SMs, grid-stride over work items.
+// folded into the magnitude.  Magnitudes go to shared memory transposed ([bin][frame]) so that the mel
+// projection runs with lane = frame and warp-uniform bands: it uses the per-band non-zero bin ranges of the basis
+// found at model creation (~2*201 FMAs per frame for a triangular filterbank, exact for any dense basis) with
+// broadcast weight reads and conflict-free magnitude reads; the [32, M] result tile leaves as one contiguous
+// block.  Persistent grid: (resident CTAs per SM) x 148 SMs, grid-stride over work items.
 #include "common.cuh"
 #include "fft400.cuh"
 
@@ -26,12 +28,17 @@ using fft::cpx;
 
 constexpr int kFePairs = 16;                         // frame pairs per work item
 constexpr int kFeThreads = kFePairs * fft::kR;       // 320
+constexpr int kFeWarps = kFeThreads / 32;            // 10
 constexpr int kFeItemFrames = 2 * kFePairs;          // 32
 constexpr int kFeBlock = 2 * kHop;                   // 320 samples between consecutive pairs
 constexpr int kFeSkew = 20;                          // floats of skew per 320-sample block
 constexpr int kFeWinSamples = kFePairs * kFeBlock + (kFft - kHop);       // 5360
-constexpr int kFeWinFloats = kFeWinSamples + kFeSkew * (kFePairs + 1);   // 5700
+constexpr int kFeWinRounds = (kFeWinSamples + kFeThreads - 1) / kFeThreads;   // 17
 constexpr int kFeItemHop = kFePairs * kFeBlock;      // 5120 samples between consecutive items of a stream
+constexpr int kFeMagStride = 33;                     // floats per bin row of the transposed magnitudes [201][33]
+// the window (5360 samples + skew) and the transposed magnitudes share one region: the window is dead after stage 1
+constexpr int kFeWinFloats = kFeWinRounds * (kFeBlock + kFeSkew);        // 5780 (position tid + 340*round)
+constexpr int kFeRegionFloats = fft::kBins * kFeMagStride > kFeWinFloats ? fft::kBins * kFeMagStride : kFeWinFloats;
 
 struct FrontendParams {
   PcmSource src;
@@ -40,7 +47,7 @@ struct FrontendParams {
   int groups;               // work items per stream = ceil(max_frames / 32)
   const int* nframes;       // [S] or null -> frames from the signal length
   int n_mel;
-  const cpx* twiddle;       // [400] k2-major (fft::twt_index)
+  const cpx* twiddle;       // [20*52] periodic k2-major table (fft::kTwSlots)
   const int* mel_start;
   const int* mel_count;
   const int* mel_offset;
@@ -57,22 +64,30 @@ struct FrontendParams {
   int* nframes_out;         // [S]
 };
 
-__device__ __forceinline__ int win_pos(int i) { return i + kFeSkew * (i / kFeBlock); }
+// Magnitude column ("frame slot") of frame fr of pair p in the transposed [bin][33] array.  Chosen so that the
+// 32 lanes of a warp in the untangle phase (consecutive columns of two adjacent pairs) hit 32 distinct banks:
+// consecutive pairs are 20 slots apart mod 32; the 2 x 16 frames still fill the 32 slots exactly once.
+__device__ __forceinline__ int mag_slot(int pair, int fr) { return ((20 * pair) & 31) + 2 * (pair >> 3) + fr; }
+// inverse: slot -> frame index 2*pair + fr within the item  (5*5 = 25 = 1 mod 8)
+__device__ __forceinline__ int slot_frame(int slot) {
+  const int pair = ((5 * (slot >> 2)) & 7) + 8 * ((slot >> 1) & 1);
+  return 2 * pair + (slot & 1);
+}
 
 __global__ void __launch_bounds__(kFeThreads, 2)
 frontend_kernel(const FrontendParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cpx* twt = reinterpret_cast<cpx*>(smem_raw);                      // [400]
-  cpx* buf = twt + fft::kN;                                         // [16][420]
-  float* win = reinterpret_cast<float*>(buf + kFePairs * fft::kBufSlots);   // [5700]
-  float* mel_w = win + kFeWinFloats;                                // [nnz]
+  cpx* twp = reinterpret_cast<cpx*>(smem_raw);                      // [1040]
+  cpx* buf = twp + fft::kTwSlots;                                   // [16][420]; later the [32][M] output tile
+  float* win = reinterpret_cast<float*>(buf + kFePairs * fft::kBufSlots);   // window, later magnitudes [201][33]
+  float* mel_w = win + kFeRegionFloats;                             // [nnz]
   int* mel_start = reinterpret_cast<int*>(mel_w + p.mel_nnz);       // [M]
   int* mel_count = mel_start + p.n_mel;
   int* mel_off = mel_count + p.n_mel;
   int* red = mel_off + p.n_mel;                                     // [16] block reduction scratch
 
-  const int tid = threadIdx.x;
-  for (int i = tid; i < fft::kN; i += kFeThreads) twt[i] = p.twiddle[i];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < fft::kTwSlots; i += kFeThreads) twp[i] = p.twiddle[i];
   for (int i = tid; i < p.mel_nnz; i += kFeThreads) mel_w[i] = p.mel_weight[i];
   for (int i = tid; i < p.n_mel; i += kFeThreads) {
     mel_start[i] = p.mel_start[i];
@@ -84,12 +99,15 @@ frontend_kernel(const FrontendParams p) {
   const int col = tid - pair * fft::kR;
   cpx* my_buf = buf + pair * fft::kBufSlots;
   const float* my_win = win + pair * (kFeBlock + kFeSkew) + col;
+  const cpx* my_tw = twp + fft::tw_base(warp, lane);
+  float* out_tile = reinterpret_cast<float*>(buf);
   const long items = p.S * p.groups;
   const bool i16 = p.src.body_dtype == KWS_PCM_I16;
+  const int M = p.n_mel;
   __syncthreads();                                    // tables staged
-  // Barriers per item: window staged | Y' exchanged | Z mirror rows published | magnitudes published.  The
-  // next item's staging only writes `win` (last read before the second barrier) and its stage 1 writes `buf`
-  // after its own first barrier, so no barrier is needed at the loop boundary.
+  // Barriers per item: window staged | Y' exchanged | Z mirror rows published | magnitudes published | mel tile
+  // complete.  The next item's staging writes the window/magnitude region (last read before the fifth barrier) and
+  // its stage 1 writes `buf` after its own first barrier, so no barrier is needed at the loop boundary.
 
   for (long item = blockIdx.x; item < items; item += gridDim.x) {
     const long s = item / p.groups;
@@ -102,69 +120,42 @@ frontend_kernel(const FrontendParams p) {
     const int q0 = g * kFeItemHop;                    // stream sample held at window position 0
     const int f0 = g * kFeItemFrames;
 
-    // ---- stage the window: stream samples [q0, q0 + 5360), zero beyond the signal
+    // ---- stage the window: stream samples [q0, q0 + 5360) -> win[i + 20*(i/320)], zero beyond the signal.
+    // Thread t takes samples t + 320*r, so the skewed position is simply t + 340*r; the loads are unit-stride
+    // across the warp and all 17 of a thread are independent (one round trip to HBM).
     int vad_acc = 0;
-    {
-      // carried tail (int16), group 0 only
-      for (int q = q0 + tid; q < head_len && q < q0 + kFeWinSamples; q += kFeThreads)
-        win[win_pos(q - q0)] = static_cast<float>(p.src.head[s * p.src.ld_head + q]);
-      int b_lo = q0 - head_len;
-      if (b_lo < 0) b_lo = 0;
-      int b_hi = q0 + kFeWinSamples - head_len;
-      if (b_hi > p.src.body_len) b_hi = p.src.body_len;
-      if (i16) {
-        const int16_t* row = static_cast<const int16_t*>(p.src.body) + s * p.src.ld_body;
-        const bool vec_ok = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
-        if (vec_ok) {
-          for (int j = (b_lo >> 3) + tid; 8 * j < b_hi; j += kFeThreads) {
-            const int b0 = 8 * j;
-            int x[8];
-            if (b0 + 8 <= p.src.body_len) {
-              const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + b0));
-              x[0] = static_cast<short>(v.x & 0xffffu); x[1] = static_cast<int>(v.x) >> 16;
-              x[2] = static_cast<short>(v.y & 0xffffu); x[3] = static_cast<int>(v.y) >> 16;
-              x[4] = static_cast<short>(v.z & 0xffffu); x[5] = static_cast<int>(v.z) >> 16;
-              x[6] = static_cast<short>(v.w & 0xffffu); x[7] = static_cast<int>(v.w) >> 16;
-            } else {
+    if (i16) {
+      const int16_t* body = static_cast<const int16_t*>(p.src.body) + s * p.src.ld_body - head_len + q0 + tid;
+      const int16_t* head = p.src.head ? p.src.head + s * p.src.ld_head + q0 + tid : nullptr;
+      int x[kFeWinRounds];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = b0 + e < p.src.body_len ? row[b0 + e] : 0;
-            }
-            int i = head_len + b0 - q0;               // window position of element 0 (may be < 0)
-            int r = (i + kFeBlock) % kFeBlock;        // i >= -7 here
-            int pos = i + kFeSkew * ((i + kFeBlock) / kFeBlock - 1);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (r == kFeBlock) {
-                r = 0;
-                pos += kFeSkew;
-              }
-              const int b = b0 + e;
-              if (b >= b_lo && b < b_hi) win[pos] = static_cast<float>(x[e]);
-              vad_acc += abs(x[e]);
-              ++pos;
-              ++r;
-            }
-          }
-        } else {
-          for (int b = b_lo + tid; b < b_hi; b += kFeThreads) {
-            const int x = row[b];
-            win[win_pos(head_len + b - q0)] = static_cast<float>(x);
-            vad_acc += abs(x);
-          }
-        }
-      } else {
-        const float* row = static_cast<const float*>(p.src.body) + s * p.src.ld_body;
-        for (int b = b_lo + tid; b < b_hi; b += kFeThreads) win[win_pos(head_len + b - q0)] = __ldg(row + b);
+      for (int r = 0; r < kFeWinRounds; ++r) {
+        const int q = q0 + tid + kFeBlock * r;
+        x[r] = 0;
+        if (q < head_len) x[r] = head[kFeBlock * r];
+        else if (q < total_len) x[r] = __ldg(body + kFeBlock * r);
       }
-      // zero fill beyond the signal
-      int z_lo = total_len - q0;
-      if (z_lo < 0) z_lo = 0;
-      for (int i = z_lo + tid; i < kFeWinSamples; i += kFeThreads) win[win_pos(i)] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < kFeWinRounds; ++r) {
+        const int q = q0 + tid + kFeBlock * r;
+        if (r < kFeWinRounds - 1 || tid < kFeWinSamples - kFeBlock * (kFeWinRounds - 1))
+          win[tid + (kFeBlock + kFeSkew) * r] = static_cast<float>(x[r]);
+        if (q >= head_len) vad_acc += abs(x[r]);
+      }
+    } else {
+      const float* body = static_cast<const float*>(p.src.body) + s * p.src.ld_body + q0 + tid;
+#pragma unroll
+      for (int r = 0; r < kFeWinRounds; ++r) {
+        const int q = q0 + tid + kFeBlock * r;
+        const float v = q < total_len ? __ldg(body + kFeBlock * r) : 0.0f;
+        if (r < kFeWinRounds - 1 || tid < kFeWinSamples - kFeBlock * (kFeWinRounds - 1))
+          win[tid + (kFeBlock + kFeSkew) * r] = v;
+      }
     }
     if (p.fuse_pre) {                                 // block sum of |x| over the chunk (exact integers)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) vad_acc += __shfl_xor_sync(0xffffffffu, vad_acc, o);
-      if ((tid & 31) == 0) red[tid >> 5] = vad_acc;
+      if (lane == 0) red[warp] = vad_acc;
     }
     __syncthreads();
 
@@ -173,11 +164,14 @@ frontend_kernel(const FrontendParams p) {
       const int keep = total_len >= kFft ? (total_len - kFft) % kHop + (kFft - kHop) : total_len;
       const int start = total_len - keep;
       int16_t* tnext = p.tail_next + s * 400;
-      for (int i = tid; i < keep; i += kFeThreads) tnext[i] = static_cast<int16_t>(win[win_pos(start + i)]);
+      for (int i = tid; i < keep; i += kFeThreads) {
+        const int w = start + i;
+        tnext[i] = static_cast<int16_t>(win[w + kFeSkew * (w / kFeBlock)]);
+      }
       if (tid == 0) {
         long long sum = 0;
 #pragma unroll
-        for (int w = 0; w < kFeThreads / 32; ++w) sum += red[w];
+        for (int w = 0; w < kFeWarps; ++w) sum += red[w];
         p.silence[s] = sum > p.vad_limit ? 0 : 1;
         p.nframes_out[s] = nfr;
         p.len_next[s] = keep;
@@ -193,35 +187,50 @@ frontend_kernel(const FrontendParams p) {
         v[n2].re = my_win[20 * n2 + (n2 >= 16 ? kFeSkew : 0)];
         v[n2].im = my_win[kHop + 20 * n2 + (n2 >= 8 ? kFeSkew : 0)];
       }
-      fft::stage1_col(col, v, twt, my_buf);
+      fft::stage1_col(col, v, my_tw, my_buf);
     }
     __syncthreads();
     if (live) fft::stage2_col(col, my_buf, v);
     __syncthreads();
-    float* mag = reinterpret_cast<float*>(my_buf);
-    if (live) fft::untangle_col(col, v, my_buf, p.mag_scale, mag);
+    // magnitudes, transposed: mag[bin*33 + slot]; the window is dead since the second barrier
+    float* mag = win;
+    if (live) fft::untangle_col(col, v, my_buf, p.mag_scale, mag + mag_slot(pair, 0), mag + mag_slot(pair, 1), kFeMagStride);
     __syncthreads();
-    if (live) {
-      const bool b_live = fa + 1 < nfr;
-      float* out_a = p.mel_out + (s * p.max_frames + fa) * p.n_mel;
-      for (int m = col; m < p.n_mel; m += fft::kR) {
+    // ---- mel projection: lane = frame slot, warp = set of bands {warp, warp+10, ...}: band ranges and weights
+    // are warp-uniform (broadcast reads, no divergence), magnitude reads are unit-stride across the lanes
+    {
+      const int fi = slot_frame(lane);
+      const float* mcol = mag + lane;
+      for (int m = warp; m < M; m += kFeWarps) {
         const int k0 = mel_start[m], c = mel_count[m];
         const float* wv = mel_w + mel_off[m];
-        float acc_a = 0.0f, acc_b = 0.0f;
-        for (int i = 0; i < c; ++i) {
-          const float wgt = wv[i];
-          acc_a = fmaf(mag[k0 + i], wgt, acc_a);
-          acc_b = fmaf(mag[fft::kMagB + k0 + i], wgt, acc_b);
-        }
-        out_a[m] = acc_a;
-        if (b_live) out_a[p.n_mel + m] = acc_b;
+        const float* mp = mcol + k0 * kFeMagStride;
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int i = 0; i < c; ++i) acc = fmaf(mp[i * kFeMagStride], wv[i], acc);
+        out_tile[fi * M + m] = acc;
+      }
+    }
+    __syncthreads();
+    // ---- the item's frames are one contiguous block of mel_out
+    {
+      int nfi = nfr - f0;
+      if (nfi > kFeItemFrames) nfi = kFeItemFrames;
+      const int total = nfi > 0 ? nfi * M : 0;
+      float* dst = p.mel_out + (s * p.max_frames + f0) * M;
+      if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0) {
+        const float4* src4 = reinterpret_cast<const float4*>(out_tile);
+        float4* dst4 = reinterpret_cast<float4*>(dst);
+        for (int i = tid; i < (total >> 2); i += kFeThreads) dst4[i] = src4[i];
+      } else {
+        for (int i = tid; i < total; i += kFeThreads) dst[i] = out_tile[i];
       }
     }
   }
 }
 
 static size_t frontend_smem_bytes(const kws_model* m) {
-  return sizeof(cpx) * fft::kN + sizeof(cpx) * kFePairs * fft::kBufSlots + sizeof(float) * kFeWinFloats +
+  return sizeof(cpx) * fft::kTwSlots + sizeof(cpx) * kFePairs * fft::kBufSlots + sizeof(float) * kFeRegionFloats +
          sizeof(float) * m->mel.nnz + sizeof(int) * 3 * m->cfg.n_mel + sizeof(int) * 16;
 }
 

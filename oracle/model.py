@@ -193,18 +193,45 @@ def _operand(a, operand_dtype, dtype):
     return a if operand_dtype is None else a.astype(operand_dtype).astype(dtype)
 
 
-def gru_cell(x, h, gates_kernel, gates_bias, cand_kernel, cand_bias, dtype=np.float32, operand_dtype=None):
+def _split_product(x, W, od, dtype):
+    """Emulation of the tensor-core path's layer-0 input projection: x = x_hi + x_lo and W = W_hi + W_lo in
+    ``od`` (fp16), product = x_hi W_hi + x_lo W_hi + x_hi W_lo accumulated in ``dtype``."""
+    xh = _operand(x, od, dtype)
+    xl = _operand((x - xh).astype(dtype), od, dtype)
+    Wh = _operand(W, od, dtype)
+    Wl = _operand((W - Wh).astype(dtype), od, dtype)
+    return np.matmul(xh, Wh) + np.matmul(xl, Wh) + np.matmul(xh, Wl)
+
+
+def gru_cell(x, h, gates_kernel, gates_bias, cand_kernel, cand_bias, dtype=np.float32, operand_dtype=None,
+             split_x=False):
     """One TF GRUCell step.  NOTE reset gate is applied to h BEFORE the
-    candidate matmul (not the cuDNN / torch.nn.GRU formulation)."""
+    candidate matmul (not the cuDNN / torch.nn.GRU formulation).
+
+    ``operand_dtype`` / ``split_x`` only model the tensor-core kernel's operand rounding (test infrastructure
+    for a tight logic check); the reference graph is ``operand_dtype=None``."""
     one = dtype(1.0)
     od = operand_dtype
-    xh = _operand(np.concatenate([x, h], axis=1), od, dtype)
-    gate_in = (np.matmul(xh, _operand(gates_kernel.astype(dtype), od, dtype)) + gates_bias.astype(dtype)).astype(dtype)
-    gates = _sigmoid(gate_in).astype(dtype)
     H = h.shape[1]
+    if od is None:
+        xh = np.concatenate([x, h], axis=1)
+        gate_in = (np.matmul(xh, gates_kernel.astype(dtype)) + gates_bias.astype(dtype)).astype(dtype)
+    else:
+        in_dim = x.shape[1]
+        Wx, Wh = gates_kernel[:in_dim].astype(dtype), gates_kernel[in_dim:].astype(dtype)
+        xp = _split_product(x, Wx, od, dtype) if split_x else np.matmul(_operand(x, od, dtype), _operand(Wx, od, dtype))
+        gate_in = (xp + np.matmul(_operand(h, od, dtype), _operand(Wh, od, dtype)) + gates_bias.astype(dtype)).astype(dtype)
+    gates = _sigmoid(gate_in).astype(dtype)
     r, u = gates[:, :H], gates[:, H:]
-    xrh = _operand(np.concatenate([x, (r * h).astype(dtype)], axis=1), od, dtype)
-    cand = (np.matmul(xrh, _operand(cand_kernel.astype(dtype), od, dtype)) + cand_bias.astype(dtype)).astype(dtype)
+    rh = (r * h).astype(dtype)
+    if od is None:
+        xrh = np.concatenate([x, rh], axis=1)
+        cand = (np.matmul(xrh, cand_kernel.astype(dtype)) + cand_bias.astype(dtype)).astype(dtype)
+    else:
+        in_dim = x.shape[1]
+        Wx, Wh = cand_kernel[:in_dim].astype(dtype), cand_kernel[in_dim:].astype(dtype)
+        xp = _split_product(x, Wx, od, dtype) if split_x else np.matmul(_operand(x, od, dtype), _operand(Wx, od, dtype))
+        cand = (xp + np.matmul(_operand(rh, od, dtype), _operand(Wh, od, dtype)) + cand_bias.astype(dtype)).astype(dtype)
     c = np.tanh(cand).astype(dtype)
     return (u * h + (one - u) * c).astype(dtype)
 
@@ -228,7 +255,8 @@ def gru_forward(x: np.ndarray, state: np.ndarray, w: Weights,
         live = None if seq_len is None else (t < np.asarray(seq_len))[:, None]
         for l in range(w.num_layers):
             new_h = gru_cell(inp, h[l], w.gates_kernel[l], w.gates_bias[l],
-                             w.cand_kernel[l], w.cand_bias[l], dtype, operand_dtype)
+                             w.cand_kernel[l], w.cand_bias[l], dtype, operand_dtype,
+                             split_x=(operand_dtype is not None and l == 0 and inp.shape[1] <= 64))
             if live is not None:
                 new_h = np.where(live, new_h, h[l])
             h[l] = new_h

@@ -6,14 +6,14 @@
 using namespace kws::fft;
 
 extern "C" void fft400_pair_mags(const float* win560, float* mag_a201, float* mag_b201) {
-  static cpx twt[kN];
+  static cpx twp[kTwSlots];
   static bool init = false;
   if (!init) {
-    for (int n1 = 0; n1 < kR; ++n1)
-      for (int k2 = 0; k2 < kR; ++k2) {
-        const double a = -2.0 * M_PI * (n1 * k2) / kN;
-        twt[twt_index(n1, k2)].re = (float)std::cos(a);
-        twt[twt_index(n1, k2)].im = (float)std::sin(a);
+    for (int k2 = 0; k2 < kR; ++k2)
+      for (int j = 0; j < kTwStride; ++j) {
+        const double a = -2.0 * M_PI * ((j % kR) * k2) / kN;
+        twp[k2 * kTwStride + j].re = (float)std::cos(a);
+        twp[k2 * kTwStride + j].im = (float)std::sin(a);
       }
     init = true;
   }
@@ -24,17 +24,12 @@ extern "C" void fft400_pair_mags(const float* win560, float* mag_a201, float* ma
       regs[c][n2].re = win560[c + 20 * n2];
       regs[c][n2].im = win560[160 + c + 20 * n2];
     }
-    stage1_col(c, regs[c], twt, buf);
+    // thread t = 20*pair + c of a CTA; emulate a pair that straddles a warp boundary (pair 1 -> t = 20 + c)
+    const int t = 20 + c;
+    stage1_col(c, regs[c], twp + tw_base(t >> 5, t & 31), buf);
   }                                                  // --- barrier ---
   for (int c = 0; c < kR; ++c) stage2_col(c, buf, regs[c]);   // --- barrier ---
-  // emulate the in-place reuse: every thread reads its mirror slots first only if no writer got there before;
-  // on the GPU the written region (rows 0..9) and the read region (rows 10..19) are disjoint, so order is free.
-  float* mag = reinterpret_cast<float*>(buf);
-  for (int c = kR - 1; c >= 0; --c) untangle_col(c, regs[c], buf, 0.5f, mag);
-  for (int k = 0; k < kBins; ++k) {
-    mag_a201[k] = mag[k];
-    mag_b201[k] = mag[kMagB + k];
-  }
+  for (int c = kR - 1; c >= 0; --c) untangle_col(c, regs[c], buf, 0.5f, mag_a201, mag_b201, 1);
 }
 
 extern "C" void dft20_host(const float* in40, float* out40) {

@@ -133,11 +133,12 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
         if (lo < 0) lo = k;
         hi = k;
       }
-    offset[b] = static_cast<int>(packed.size());
+    offset[b] = static_cast<int>(packed.size());                      // always a multiple of 4 (float4 reads)
     if (lo >= 0) {
       start[b] = lo;
-      count[b] = hi - lo + 1;
-      for (int k = lo; k <= hi; ++k) packed.push_back(w->mel_basis[static_cast<size_t>(k) * M + b]);
+      count[b] = (hi - lo + 1 + 3) / 4 * 4;                           // padded with zero weights
+      for (int k = lo; k < lo + count[b]; ++k)
+        packed.push_back(k <= hi ? w->mel_basis[static_cast<size_t>(k) * M + b] : 0.0f);
     }
     if (count[b] > m->mel.max_count) m->mel.max_count = count[b];
   }

@@ -38,7 +38,10 @@ constexpr int kFeItemHop = kFePairs * kFeBlock;      // 5120 samples between con
 constexpr int kFeMagStride = 33;                     // floats per bin row of the transposed magnitudes [201][33]
 // the window (5360 samples + skew) and the transposed magnitudes share one region: the window is dead after stage 1
 constexpr int kFeWinFloats = kFeWinRounds * (kFeBlock + kFeSkew);        // 5780 (position tid + 340*round)
-constexpr int kFeRegionFloats = fft::kBins * kFeMagStride > kFeWinFloats ? fft::kBins * kFeMagStride : kFeWinFloats;
+constexpr int kFeMagRows = fft::kBins + 3;           // band ranges are padded to multiples of 4 bins: rows 201..203 stay zero
+constexpr int kFeRegionFloats = kFeMagRows * kFeMagStride > kFeWinFloats ? kFeMagRows * kFeMagStride : kFeWinFloats;
+static_assert(kFeWinFloats <= fft::kBins * kFeMagStride, "the window must not reach the zero rows");
+static_assert((kFeRegionFloats * 4) % 16 == 0, "mel weights follow the region and are read as float4");
 
 struct FrontendParams {
   PcmSource src;
@@ -94,6 +97,7 @@ frontend_kernel(const FrontendParams p) {
     mel_count[i] = p.mel_count[i];
     mel_off[i] = p.mel_offset[i];
   }
+  for (int i = fft::kBins * kFeMagStride + tid; i < kFeRegionFloats; i += kFeThreads) win[i] = 0.0f;
 
   const int pair = tid / fft::kR;
   const int col = tid - pair * fft::kR;
@@ -124,23 +128,41 @@ frontend_kernel(const FrontendParams p) {
     // Thread t takes samples t + 320*r, so the skewed position is simply t + 340*r; the loads are unit-stride
     // across the warp and all 17 of a thread are independent (one round trip to HBM).
     int vad_acc = 0;
+    const bool last_ok = tid < kFeWinSamples - kFeBlock * (kFeWinRounds - 1);   // the 17th round is partial
     if (i16) {
       const int16_t* body = static_cast<const int16_t*>(p.src.body) + s * p.src.ld_body - head_len + q0 + tid;
-      const int16_t* head = p.src.head ? p.src.head + s * p.src.ld_head + q0 + tid : nullptr;
-      int x[kFeWinRounds];
-#pragma unroll
-      for (int r = 0; r < kFeWinRounds; ++r) {
+      const int16_t* head = p.src.head + s * p.src.ld_head + q0 + tid;          // only dereferenced below head_len
+      // generic element: carried tail, chunk, or zero beyond the signal
+      auto fetch = [&](int r) {
         const int q = q0 + tid + kFeBlock * r;
-        x[r] = 0;
-        if (q < head_len) x[r] = head[kFeBlock * r];
-        else if (q < total_len) x[r] = __ldg(body + kFeBlock * r);
-      }
+        const bool in_head = q < head_len;
+        const int16_t* ptr = in_head ? head + kFeBlock * r : body + kFeBlock * r;
+        int x = 0;
+        if (q < total_len) x = *ptr;
+        return x;
+      };
+      // rounds 2..14 hold samples [q0+640, q0+4800): entirely inside the chunk for every steady-state item
+      const bool fast = q0 + 2 * kFeBlock >= head_len && q0 + 15 * kFeBlock <= total_len;
+      if (fast) {
+        int x[kFeWinRounds];
+        x[0] = fetch(0);
+        x[1] = fetch(1);
 #pragma unroll
-      for (int r = 0; r < kFeWinRounds; ++r) {
-        const int q = q0 + tid + kFeBlock * r;
-        if (r < kFeWinRounds - 1 || tid < kFeWinSamples - kFeBlock * (kFeWinRounds - 1))
-          win[tid + (kFeBlock + kFeSkew) * r] = static_cast<float>(x[r]);
-        if (q >= head_len) vad_acc += abs(x[r]);
+        for (int r = 2; r < 15; ++r) x[r] = __ldg(body + kFeBlock * r);
+        x[15] = fetch(15);
+        x[16] = last_ok ? fetch(16) : 0;
+#pragma unroll
+        for (int r = 0; r < kFeWinRounds; ++r) {
+          if (r < kFeWinRounds - 1 || last_ok) win[tid + (kFeBlock + kFeSkew) * r] = static_cast<float>(x[r]);
+          if (r >= 2 || q0 + tid + kFeBlock * r >= head_len) vad_acc += abs(x[r]);
+        }
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < kFeWinRounds; ++r) {
+          const int x = (r < kFeWinRounds - 1 || last_ok) ? fetch(r) : 0;
+          if (r < kFeWinRounds - 1 || last_ok) win[tid + (kFeBlock + kFeSkew) * r] = static_cast<float>(x);
+          if (q0 + tid + kFeBlock * r >= head_len) vad_acc += abs(x);
+        }
       }
     } else {
       const float* body = static_cast<const float*>(p.src.body) + s * p.src.ld_body + q0 + tid;
@@ -148,8 +170,7 @@ frontend_kernel(const FrontendParams p) {
       for (int r = 0; r < kFeWinRounds; ++r) {
         const int q = q0 + tid + kFeBlock * r;
         const float v = q < total_len ? __ldg(body + kFeBlock * r) : 0.0f;
-        if (r < kFeWinRounds - 1 || tid < kFeWinSamples - kFeBlock * (kFeWinRounds - 1))
-          win[tid + (kFeBlock + kFeSkew) * r] = v;
+        if (r < kFeWinRounds - 1 || last_ok) win[tid + (kFeBlock + kFeSkew) * r] = v;
       }
     }
     if (p.fuse_pre) {                                 // block sum of |x| over the chunk (exact integers)
@@ -205,9 +226,17 @@ frontend_kernel(const FrontendParams p) {
         const int k0 = mel_start[m], c = mel_count[m];
         const float* wv = mel_w + mel_off[m];
         const float* mp = mcol + k0 * kFeMagStride;
-        float acc = 0.0f;
-#pragma unroll 4
-        for (int i = 0; i < c; ++i) acc = fmaf(mp[i * kFeMagStride], wv[i], acc);
+        // ranges are padded to a multiple of 4 bins with zero weights (api.cu); the rows past bin 200 are zero
+        float acc0 = 0.0f, acc1 = 0.0f;
+        for (int i = 0; i < c; i += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wv + i);
+          acc0 = fmaf(mp[0], w4.x, acc0);
+          acc1 = fmaf(mp[kFeMagStride], w4.y, acc1);
+          acc0 = fmaf(mp[2 * kFeMagStride], w4.z, acc0);
+          acc1 = fmaf(mp[3 * kFeMagStride], w4.w, acc1);
+          mp += 4 * kFeMagStride;
+        }
+        const float acc = acc0 + acc1;
         out_tile[fi * M + m] = acc;
       }
     }

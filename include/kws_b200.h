@@ -235,6 +235,10 @@ int kws_positional_encoding(int32_t max_position, int32_t encoding_size, float* 
 int kws_debug_tc_gemm(const float* A, const float* B_host, float* D, int N, int K, int ss_mode,
                       void* stream);
 
+/* Debug: enable/disable and read the phase timeline (SM clock ticks) of the first tile of CTA 0 of the last
+ * tensor-core GRU launch; see csrc/gru_tc.cu.  host_out may be NULL (only set the switch).               */
+int kws_debug_tc_timeline(int enable, long long* host_out, int count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,7 @@ _SIGNATURES = {
     "kws_octize_weight": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
     "kws_positional_encoding": (c_int, [c_int32, c_int32, c_void_p, c_void_p]),
     "kws_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kws_debug_tc_timeline": (c_int, [c_int, c_void_p, c_int]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

@@ -230,8 +230,8 @@ extern "C" int kws_model_reserve(kws_model* m, int64_t max_streams, int32_t max_
   m->scratch_mel = m->scratch_seq = nullptr;
   m->cap_streams = 0;
   m->cap_frames = 0;
-  const size_t mel_elems = static_cast<size_t>(S) * n * m->cfg.n_mel;
-  const size_t tiles = static_cast<size_t>(ceil_div(S, 64));
+  const size_t mel_elems = mel_scratch_elems(S, n, m->cfg.n_mel);
+  const size_t tiles = static_cast<size_t>(ceil_div(S, 128) * 2);
   const int nbuf = m->cfg.num_layers > 2 ? 2 : 1;
   const size_t seq_elems = tiles * n * kHidden * 64 * nbuf;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->scratch_mel), sizeof(float) * (mel_elems ? mel_elems : 1));
@@ -321,7 +321,20 @@ extern "C" int kws_deploy_forward(kws_model* m, const void* pcm, int pcm_dtype, 
   src.body_dtype = pcm_dtype;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KWS_CUDA_OK(cudaSetDevice(m->device));
-  rc = launch_frontend(m, src, S, n, nullptr, m->scratch_mel, st);
+  const bool tiled = mel_can_tile(m);
+  rc = launch_frontend(m, src, S, n, nullptr, m->scratch_mel, st, nullptr, tiled);
   if (rc != KWS_OK) return rc;
-  return kws_gru_forward(m, m->scratch_mel, S, n, nullptr, state_in, probs_out, state_out, logits_out, stream);
+  KWS_REQUIRE(state_in && state_out && probs_out, "state / probs pointer is NULL");
+  KWS_REQUIRE(reinterpret_cast<uintptr_t>(state_in) % 16 == 0 && reinterpret_cast<uintptr_t>(state_out) % 16 == 0,
+              "state pointers must be 16-byte aligned");
+  GruArgs a;
+  a.x = m->scratch_mel;
+  a.x_tiled = tiled;
+  a.S = S;
+  a.n = n;
+  a.state_in = state_in;
+  a.state_out = state_out;
+  a.probs = probs_out;
+  a.logits = logits_out;
+  return launch_gru(m, a, st);
 }

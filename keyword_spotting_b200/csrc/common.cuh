@@ -116,12 +116,20 @@ struct FrontendPre {
   int32_t* nframes_out = nullptr;     // [S]
 };
 bool frontend_can_fuse_pre(int chunk_len, int tail_cap);
+// Stream-tiled mel scratch (front end -> tensor-core GRU): float4 chunk c (of Q = M/4) of frame t of stream s sits at
+// float4 index ((s/128 * n + t) * Q + c) * 128 + s % 128, so the 128 threads of a GRU tile read, and the front end
+// writes, 16-byte pieces that are contiguous across streams.  Size: ceil(S/128)*128 * n * M floats.
+inline bool mel_can_tile(const kws_model* m) { return m->precision == KWS_PRECISION_TC_FP16 && m->cfg.n_mel % 4 == 0; }
+inline size_t mel_scratch_elems(int64_t S, int32_t n, int n_mel) {
+  return static_cast<size_t>(ceil_div(S, 128) * 128) * static_cast<size_t>(n > 0 ? n : 1) * n_mel;
+}
 int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t max_frames,
                     const int32_t* nframes /*[S] or null*/, float* mel_out, cudaStream_t st,
-                    const FrontendPre* pre = nullptr);
+                    const FrontendPre* pre = nullptr, bool tiled_out = false);
 
 struct GruArgs {
-  const float* x = nullptr;       // layer-0 input [S, n, M] row-major
+  const float* x = nullptr;       // layer-0 input [S, n, M] row-major, or stream-tiled when x_tiled
+  bool x_tiled = false;           // mel_tiled_offset layout (tensor-core path, M % 4 == 0)
   int64_t S = 0;
   int32_t n = 0;
   const int32_t* seq_len = nullptr;       // [S] or null

@@ -56,7 +56,8 @@ struct FrontendParams {
   const int* mel_offset;
   const float* mel_weight;
   int mel_nnz;
-  float* mel_out;           // [S, max_frames, n_mel]
+  float* mel_out;           // [S, max_frames, n_mel], or stream-tiled (common.cuh) when tiled_out
+  int tiled_out;
   float mag_scale;          // 0.5 * (int16 input ? 2^-15 : 1)
   // fused server pre-step (only with groups == 1 and int16 input): VAD, frame count, next tail
   int fuse_pre;
@@ -246,13 +247,21 @@ frontend_kernel(const FrontendParams p) {
       int nfi = nfr - f0;
       if (nfi > kFeItemFrames) nfi = kFeItemFrames;
       const int total = nfi > 0 ? nfi * M : 0;
-      float* dst = p.mel_out + (s * p.max_frames + f0) * M;
-      if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0) {
+      if (p.tiled_out) {
+        // float4 chunk c of frame f -> ((tile*n + f)*Q + c)*128 + stream%128
+        const int Q = M >> 2;
         const float4* src4 = reinterpret_cast<const float4*>(out_tile);
-        float4* dst4 = reinterpret_cast<float4*>(dst);
-        for (int i = tid; i < (total >> 2); i += kFeThreads) dst4[i] = src4[i];
+        float4* dst4 = reinterpret_cast<float4*>(p.mel_out) + ((s >> 7) * p.max_frames + f0) * static_cast<long>(Q) * 128 + (s & 127);
+        for (int i = tid; i < (total >> 2); i += kFeThreads) dst4[static_cast<long>(i) * 128] = src4[i];
       } else {
-        for (int i = tid; i < total; i += kFeThreads) dst[i] = out_tile[i];
+        float* dst = p.mel_out + (s * p.max_frames + f0) * M;
+        if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0) {
+          const float4* src4 = reinterpret_cast<const float4*>(out_tile);
+          float4* dst4 = reinterpret_cast<float4*>(dst);
+          for (int i = tid; i < (total >> 2); i += kFeThreads) dst4[i] = src4[i];
+        } else {
+          for (int i = tid; i < total; i += kFeThreads) dst[i] = out_tile[i];
+        }
       }
     }
   }
@@ -268,7 +277,7 @@ bool frontend_can_fuse_pre(int chunk_len, int tail_cap) {
 }
 
 int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t max_frames,
-                    const int32_t* nframes, float* mel_out, cudaStream_t st, const FrontendPre* pre) {
+                    const int32_t* nframes, float* mel_out, cudaStream_t st, const FrontendPre* pre, bool tiled_out) {
   if (S <= 0) return KWS_OK;
   if (max_frames <= 0 && !pre) return KWS_OK;
   FrontendParams p;
@@ -285,6 +294,8 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
   p.mel_weight = m->mel.weight;
   p.mel_nnz = m->mel.nnz;
   p.mel_out = mel_out;
+  p.tiled_out = tiled_out ? 1 : 0;
+  if (tiled_out && (m->cfg.n_mel & 3)) return fail(KWS_ERR_INVALID_ARGUMENT, "tiled mel output needs n_mel % 4 == 0");
   p.mag_scale = src.body_dtype == KWS_PCM_I16 ? 0.5f / 32768.0f : 0.5f;
   p.fuse_pre = 0;
   p.vad_limit = 0;

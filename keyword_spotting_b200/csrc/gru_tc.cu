@@ -7,16 +7,27 @@
 //   * one CTA owns 128 streams for a whole layer -- the streams are the M dimension of tcgen05.mma
 //     (M=128, cta_group::1); the TMEM lane of a stream is owned by the same thread for the whole chunk, so the
 //     fp32 master state h never leaves registers between time steps;
-//   * all weights of the layer ([384, in+128] fp16, 135-196 KB) are resident in shared memory for the whole
+//   * all weights of the layer ([384, K] fp16, 135-196 KB) are resident in shared memory for the whole
 //     kernel, in the K-major SWIZZLE_NONE canonical layout, packed on the host at model creation;
 //   * the A operand [x_t | h_{t-1}] (and [x_t | r*h]) lives in TENSOR MEMORY (TS-form MMA): each thread writes
 //     its own stream's row with tcgen05.st, so activations never touch shared memory and no proxy fence is
-//     needed.  TMEM map (512 columns): D_gates 0..255 (r | u), D_cand 256..383, A_x, A_h;
+//     needed.  TMEM map (512 columns): D_r 0..127, D_u 128..255, D_cand 256..383, A_x, A_h;
 //   * the input projection is not a separate GEMM: x_t W[0:in] is accumulated into the same TMEM tile as
-//     h W[in:], and the candidate's x-part MMAs are issued right behind the gate MMAs so they run under
-//     the gate epilogue;
-//   * per step: 16+8+8 MMAs issued by one thread, two tcgen05.commit -> mbarrier hand-offs, two CTA barriers;
-//     256 threads = two warpgroups that split the 128 hidden units; gate algebra in fp32 with ex2/rcp.
+//     h W[in:], and it is issued a phase early so it never sits on the recurrent critical path;
+//   * warp-specialised: warps 0-7 (two warpgroups that split the 128 hidden units) run the gate algebra from
+//     TMEM; warp 8 only issues MMAs.  Everything is handed over with mbarriers (tcgen05.commit one way,
+//     256-thread arrivals the other) -- no CTA-wide barrier inside the time loop.  Per step:
+//         MMA warp                                   epilogue threads
+//         r-gate x-part             <- A_x ready     ...
+//         r-gate h-part -> commit R <- A_h ready
+//         u-gate x+h    -> commit U                  wait R: r = sigmoid(D_r), keep fp16(r*h) in registers
+//         cand  x-part                               wait U: A_h <- r*h, arrive;  D_u <- u = sigmoid(D_u) in place
+//         cand  h-part  -> commit C <- A_rh ready    wait C: A_x <- x_{t+1}, arrive (next r-gate x-part overlaps)
+//                                                    c = tanh(D_c), h' = c + u (h - c), FC partials, A_h <- h', arrive
+//     so the dependent chain of a step is  r-MMA(h) -> sigmoid -> cand-MMA(h) -> tanh,  with the u gate, all
+//     x-part MMAs, the softmax and the global loads/stores running beside it;
+//   * gate algebra in fp32 with ex2.approx / rcp.approx (2 MUFU per activation, 6 per hidden unit and step --
+//     the unit this kernel is bound by), biases pre-scaled by log2(e) so an activation is FFMA, EX2, FADD, RCP.
 // Operands are fp16 (weights rounded once on the host, activations rounded when written to TMEM), accumulation
 // and all state fp32.  The layer-0 input projection is the exception: mel features are unbounded (tens for loud
 // audio) and a single fp16 rounding of x and W_x alone costs up to 3e-3 on the carried state, so that product is
@@ -31,8 +42,10 @@
 namespace kws {
 
 constexpr int kTcTile = 128;
-constexpr int kTcThreads = 256;
-constexpr int kTcUnits = kHidden / 2;     // hidden units per thread (warpgroup split)
+constexpr int kTcEpiThreads = 256;        // warps 0-7: gate algebra
+constexpr int kTcThreads = 384;           // + warpgroup 2: warp 8 issues the MMAs (warps 9-11 only donate registers)
+constexpr int kTcUnits = kHidden / 2;     // hidden units per epilogue thread (warpgroup split)
+constexpr int kTcMaxClasses = 8;          // FC columns kept per thread
 
 struct GruTcParams {
   int kx;                      // x width padded to a multiple of 16
@@ -40,9 +53,10 @@ struct GruTcParams {
   int in_dim;                  // true x width
   long S;
   int n;
-  const float* x_f32;          // layer 0: [S, n, in_dim] fp32 (mel)
-  const __half* x_f16;         // layer > 0: [S, n, 128] fp16
-  __half* y_f16;               // non-last layers: [S, n, 128] fp16
+  const float* x_f32;          // layer 0: mel fp32, [S, n, in_dim] row-major or stream-tiled (x_tiled, see common.cuh)
+  int x_tiled;
+  const __half* x_f16;         // layer > 0: fp16, stream-tiled [tile][t][16 chunks][128 streams][8 units]
+  __half* y_f16;               // non-last layers: same tiled layout
   const __half* wpack;         // [384, kxw+128] fp16, canonical layout: [Wx_hi | Wx_lo (split only) | Wh]
   const float* bias;           // [384] = gates (r | u) | candidate
   const float* h_in;           // [S, 128]
@@ -54,14 +68,49 @@ struct GruTcParams {
   int C;
   float* probs;                // [S, n, C]
   float* logits;               // [S, n, C] or null
+  int timeline;                // record g_tc_timeline (debug)
 };
 
-__device__ __forceinline__ float fast_sigmoid(float x) {
-  return __fdividef(1.0f, 1.0f + __expf(-x));          // ex2.approx + rcp.approx: ~1e-7 absolute
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float fast_tanh(float x) {
-  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+// sigmoid(a + b) with nb = -log2(e) * b:   1 / (1 + 2^(-log2e*(a+b)))         FFMA, EX2, FADD, RCP
+__device__ __forceinline__ float sigmoid_pre(float a, float nb) {
+  return rcp_approx(1.0f + ex2_approx(fmaf(a, -kLog2e, nb)));
+}
+// tanh(a + b) with pb = 2*log2(e) * b:     1 - 2 / (1 + 2^(2*log2e*(a+b)))    FFMA, EX2, FADD, RCP, FFMA
+__device__ __forceinline__ float tanh_pre(float a, float pb) {
+  return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(fmaf(a, 2.0f * kLog2e, pb))), 1.0f);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// this thread's TMEM stores are complete and ordered before the arrival
+__device__ __forceinline__ void tmem_publish(uint64_t* bar) {
+  tc::wait_st();
+  tc::fence_before_sync();
+  mbar_arrive(bar);
+}
+__device__ __forceinline__ void mbar_acquire(uint64_t* bar, uint32_t parity) {
+  tc::mbar_wait(bar, parity);
+  tc::fence_after_sync();
+}
+
+// Optional phase timeline of the first tile of CTA 0 (clock64 at each hand-over), for kws_debug_tc_timeline.
+__device__ long long g_tc_timeline[64 * 8];
+static int g_tc_timeline_on = 0;
+
+enum { kBarAX = 0, kBarAH, kBarARH, kBarR, kBarU, kBarC, kNumBars };
 
 // kFirst: layer 0 -- x is fp32 (mel) and its projection uses the 3-term split.
 template <bool kLast, bool kFirst>
@@ -70,32 +119,37 @@ gru_tc_kernel(const GruTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int ktot = p.kxw + kHidden;                                                  // K extent of the packed weights
   unsigned char* sW = smem;                                                         // [384, ktot] fp16
-  float* sBias = reinterpret_cast<float*>(smem + static_cast<size_t>(384) * ktot * 2);   // [384]
+  float* sBias = reinterpret_cast<float*>(smem + static_cast<size_t>(384) * ktot * 2);   // [384] pre-scaled
   float* sFcw = sBias + 384;                                                        // [128][8]
-  float* sFcb = sFcw + kHidden * 8;                                                 // [8]
-  float* sXch = sFcb + 8;                                                           // [128][8] FC partials of warpgroup 1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + kTcTile * 8);                 // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* sFcb = sFcw + kHidden * kTcMaxClasses;                                     // [8]
+  float* sXch = sFcb + kTcMaxClasses;                                               // [128][8] FC partials of warpgroup 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + kTcTile * kTcMaxClasses);     // [kNumBars]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
-  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, row = tid & 127;
+  const int tid = threadIdx.x, warp = tid >> 5;
 
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
-    tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[kBarAX], kTcEpiThreads);
+    tc::mbar_init(&bars[kBarAH], kTcEpiThreads);
+    tc::mbar_init(&bars[kBarARH], kTcEpiThreads);
+    tc::mbar_init(&bars[kBarR], 1);
+    tc::mbar_init(&bars[kBarU], 1);
+    tc::mbar_init(&bars[kBarC], 1);
     tc::mbar_fence_init();
   }
   {
     const int n16 = 384 * ktot * 2 / 16;
     const uint4* src = reinterpret_cast<const uint4*>(p.wpack);
     for (int i = tid; i < n16; i += kTcThreads) reinterpret_cast<uint4*>(sW)[i] = __ldg(src + i);
-    for (int i = tid; i < 384; i += kTcThreads) sBias[i] = p.bias[i];
+    for (int i = tid; i < 384; i += kTcThreads)
+      sBias[i] = p.bias[i] * (i < 2 * kHidden ? -kLog2e : 2.0f * kLog2e);
     if (kLast) {
-      for (int i = tid; i < kHidden * 8; i += kTcThreads) {
-        const int j = i >> 3, c = i & 7;
+      for (int i = tid; i < kHidden * kTcMaxClasses; i += kTcThreads) {
+        const int j = i / kTcMaxClasses, c = i % kTcMaxClasses;
         sFcw[i] = c < p.C ? p.fc_w[j * p.C + c] : 0.0f;
       }
-      if (tid < 8) sFcb[tid] = tid < p.C ? p.fc_b[tid] : 0.0f;
+      if (tid < kTcMaxClasses) sFcb[tid] = tid < p.C ? p.fc_b[tid] : 0.0f;
     }
   }
   tc::fence_proxy_async();            // weights written with generic stores, read by the MMA (async proxy)
@@ -104,276 +158,380 @@ gru_tc_kernel(const GruTcParams p) {
   tc::fence_after_sync();
 
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t colDg = 0, colDc = 256, colAx = 384;
-  const uint32_t colAxl = colAx + p.kx / 2;                       // x_lo (kFirst only)
+  const uint32_t colDr = 0, colDu = 128, colDc = 256, colAx = 384;
+  const uint32_t colAxl = colAx + p.kx / 2;                       // x_lo (split only)
   const bool split = kFirst && p.kxw != p.kx;                     // 3-term x product (needs 2*kx/2 + 64 <= 128 columns)
   const uint32_t colAh = colAx + p.kxw / 2;
-  const uint32_t my_ah = tmem + lane_sel + colAh + 32 * wg;      // this thread's 64 units = 32 columns
-  const int xq = p.kx / 16;                                       // st4 groups of x per warpgroup
-  const uint32_t my_ax = tmem + lane_sel + colAx + (p.kx / 4) * wg;
-  const uint32_t sbo = static_cast<uint32_t>(ktot / 8) * 128;
-  const uint32_t sW_addr = tc::smem_u32(sW);
-  const uint32_t idesc_g = tc::idesc_f16(128, 256), idesc_c = tc::idesc_f16(128, 128);
   const long ntiles = (p.S + kTcTile - 1) / kTcTile;
-  uint32_t phase = 0;                                             // parity of both mbarriers (one completion each per step)
-  const int u0 = 64 * wg;                                         // first hidden unit of this thread
 
-  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long s = tile * kTcTile + row;
-    const bool ok = s < p.S;
-    const int len = ok ? (p.seq_len ? p.seq_len[s] : p.n) : 0;
-    float h[kTcUnits];
-    {
-      const bool zero = !ok || (p.zero_state && p.zero_state[s]);
-      const float4* src = reinterpret_cast<const float4*>(p.h_in + (ok ? s : 0) * kHidden + u0);
+  if (warp >= 8) {
+    // =========================================================== MMA issuer (one elected lane of warp 8)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 8) {
+      const uint32_t sbo = static_cast<uint32_t>(ktot / 8) * 128;
+      const uint32_t idesc128 = tc::idesc_f16(128, 128);
+      const int nx = p.kx / 16, nxw = p.kxw / 16;
+      const bool lead = (tid & 31) == 0;
+      // All operand addresses are computed warp-uniformly (they live in uniform registers); only the MMA itself is
+      // predicated on the elected lane.  B descriptor of K-chunk k16 for the weight rows starting at row0 =
+      // base + ((row0/8)*sbo + 256*k16)/16 added to the 14-bit start-address field (shared memory < 256 KB: no carry).
+      const uint64_t wbase = tc::smem_desc(tc::smem_u32(sW), 128, sbo);
+      const uint32_t row_step = (16 * sbo) >> 4;                             // 128 output rows
+      // x-part of a product into D columns `dcol` (overwrites D), weight rows starting at 128*rblk
+      auto issue_x = [&](uint32_t dcol, int rblk) {
+        const uint64_t wrow = wbase + rblk * row_step;
+        for (int k16 = 0; k16 < nx; ++k16)                                   // x_hi * Wx_hi
+          if (lead) tc::mma_ts(tmem + dcol, tmem + colAx + 8 * k16, wrow + 16 * k16, idesc128, k16 > 0);
+        if (split) {
+          for (int k16 = 0; k16 < nx; ++k16)                                 // x_lo * Wx_hi
+            if (lead) tc::mma_ts(tmem + dcol, tmem + colAxl + 8 * k16, wrow + 16 * k16, idesc128, true);
+          for (int k16 = 0; k16 < nx; ++k16)                                 // x_hi * Wx_lo
+            if (lead) tc::mma_ts(tmem + dcol, tmem + colAx + 8 * k16, wrow + 16 * (nx + k16), idesc128, true);
+        }
+      };
+      auto issue_h = [&](uint32_t dcol, int rblk) {                          // += A_h * Wh[128*rblk .. +127]
+        const uint64_t wrow = wbase + rblk * row_step + 16 * nxw;
 #pragma unroll
-      for (int i = 0; i < kTcUnits / 4; ++i) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!zero) v = src[i];
-        h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+        for (int k16 = 0; k16 < kHidden / 16; ++k16)
+          if (lead) tc::mma_ts(tmem + dcol, tmem + colAh + 8 * k16, wrow + 16 * k16, idesc128, true);
+      };
+      uint32_t it = 0;
+      for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int t = 0; t < p.n; ++t, ++it) {
+          const uint32_t par = it & 1;
+          mbar_acquire(&bars[kBarAX], par);
+          issue_x(colDr, 0);                                                 // r gate, x-part (D_r is free since the last r epilogue)
+          mbar_acquire(&bars[kBarAH], par);
+          issue_h(colDr, 0);
+          if (lead) tc::commit(&bars[kBarR]);
+          issue_x(colDu, 1);                                                 // u gate: D_u held the activated u until now
+          issue_h(colDu, 1);
+          if (lead) tc::commit(&bars[kBarU]);
+          issue_x(colDc, 2);                                                 // candidate, x-part
+          mbar_acquire(&bars[kBarARH], par);
+          issue_h(colDc, 2);
+          if (lead) tc::commit(&bars[kBarC]);
+          __syncwarp();
+        }
       }
     }
-    // ---- A_h <- fp16(h);  A_x <- x_0
+  } else {
+    // =========================================================== gate algebra (256 threads, one stream each x 64 units)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");      // launched at 168: 128 x (168-72) released = 256 x (216-168) acquired
+    const int wg = tid >> 7, row = tid & 127;
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t my_ah = tmem + lane_sel + colAh + 32 * wg;      // this thread's 64 units = 32 columns
+    const int xq = p.kx / 16;                                       // st4 groups of x per warpgroup
+    const uint32_t my_ax = tmem + lane_sel + colAx + (p.kx / 4) * wg;
+    const int u0 = 64 * wg;                                         // first hidden unit of this thread
+    const float* bR = sBias + u0;
+    const float* bU = sBias + kHidden + u0;
+    const float* bC = sBias + 2 * kHidden + u0;
+    const bool x_vec = kFirst && (p.in_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x_f32) & 15) == 0;
+    uint32_t it = 0;
+
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long s = tile * kTcTile + row;
+      const bool ok = s < p.S;
+      const long sr = ok ? s : 0;
+      const int len = ok ? (p.seq_len ? p.seq_len[s] : p.n) : 0;
+      const bool all_live = __all_sync(0xffffffffu, len >= p.n);     // warp-uniform: no select in the update
+      float h[kTcUnits];
+      {
+        const bool zero = !ok || (p.zero_state && p.zero_state[s]);
+        const float4* src = reinterpret_cast<const float4*>(p.h_in + sr * kHidden + u0);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = tc::pack_half2(h[32 * c + 2 * i], h[32 * c + 2 * i + 1]);
-      tc::st16(my_ah + 16 * c, v);
-    }
-    uint32_t xr[32];                                             // x_t of this thread's half of the row, packed fp16 pairs
-    uint32_t xl[kFirst ? 32 : 1];                                // residuals x - fp16(x) (kFirst only)
-    auto load_x = [&](int t) {
-      if (!kFirst) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.x_f16 + ((ok ? s : 0) * p.n + t) * static_cast<long>(kHidden) + u0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (ok) v = __ldg(src + q);
-          xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+        for (int i = 0; i < kTcUnits / 4; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!zero) v = src[i];
+          h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
         }
-      } else {
-        const float* src = p.x_f32 + ((ok ? s : 0) * p.n + t) * static_cast<long>(p.in_dim);
-        const int k0 = (p.kx / 2) * wg;
+      }
+      uint32_t xr[32];                                             // x_t of this thread's half of the row, packed fp16 pairs
+      uint32_t xl[kFirst ? 32 : 1];                                // residuals x - fp16(x) (split only)
+      auto load_x = [&](int t) {
+        if (!kFirst) {
+          // chunk q of stream `row` sits at ((tile*n + t)*16 + q)*128 + row: a warp reads 512 contiguous bytes
+          const uint4* src = reinterpret_cast<const uint4*>(p.x_f16) + ((tile * p.n + t) * 16 + 8 * wg) * kTcTile + row;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q < xq) {
+          for (int q = 0; q < 8; ++q) {
+            const uint4 v = __ldg(src + q * kTcTile);
+            xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+          }
+        } else {
+          const float* src = p.x_f32 + (sr * p.n + t) * static_cast<long>(p.in_dim);
+          const int k0 = (p.kx / 2) * wg;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int k = k0 + 8 * q + 2 * i;
-              const float a = (ok && k < p.in_dim) ? __ldg(src + k) : 0.0f;
-              const float b = (ok && k + 1 < p.in_dim) ? __ldg(src + k + 1) : 0.0f;
-              const __half2 hi = __floats2half2_rn(a, b);
-              const float2 back = __half22float2(hi);
-              xr[4 * q + i] = *reinterpret_cast<const uint32_t*>(&hi);
-              xl[kFirst ? 4 * q + i : 0] = tc::pack_half2(a - back.x, b - back.y);
+          for (int q = 0; q < 8; ++q) {
+            if (q < xq) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = 0.0f;
+              const int k = k0 + 8 * q;
+              if (p.x_tiled) {
+                // float4 chunk c of stream `row` sits at ((tile*n + t)*Q + c)*128 + row, Q = in_dim/4
+                const float4* src4 = reinterpret_cast<const float4*>(p.x_f32) + (tile * p.n + t) * static_cast<long>(p.in_dim / 4) * kTcTile + row;
+                if (k < p.in_dim) {
+                  const float4 v = __ldg(src4 + (k / 4) * kTcTile);
+                  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+                }
+                if (k + 4 < p.in_dim) {
+                  const float4 v = __ldg(src4 + (k / 4 + 1) * kTcTile);
+                  f[4] = v.x; f[5] = v.y; f[6] = v.z; f[7] = v.w;
+                }
+              } else if (ok) {
+                if (x_vec) {
+                  if (k < p.in_dim) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+                    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+                  }
+                  if (k + 4 < p.in_dim) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + k + 4));
+                    f[4] = v.x; f[5] = v.y; f[6] = v.z; f[7] = v.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (k + i < p.in_dim) f[i] = __ldg(src + k + i);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __half2 hi = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                const float2 back = __half22float2(hi);
+                xr[4 * q + i] = *reinterpret_cast<const uint32_t*>(&hi);
+                xl[kFirst ? 4 * q + i : 0] = tc::pack_half2(f[2 * i] - back.x, f[2 * i + 1] - back.y);
+              }
             }
           }
         }
-      }
-    };
-    auto store_x = [&]() {
+      };
+      auto store_x = [&]() {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q < xq) {
-          const uint32_t v[4] = {xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]};
-          tc::st4(my_ax + 4 * q, v);
-          if (split) {
-            const uint32_t w[4] = {xl[kFirst ? 4 * q : 0], xl[kFirst ? 4 * q + 1 : 0], xl[kFirst ? 4 * q + 2 : 0],
-                                   xl[kFirst ? 4 * q + 3 : 0]};
-            tc::st4(my_ax + p.kx / 2 + 4 * q, w);
+        for (int q = 0; q < 8; ++q)
+          if (q < xq) {
+            const uint32_t v[4] = {xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]};
+            tc::st4(my_ax + 4 * q, v);
+            if (split) {
+              const uint32_t w[4] = {xl[kFirst ? 4 * q : 0], xl[kFirst ? 4 * q + 1 : 0], xl[kFirst ? 4 * q + 2 : 0],
+                                     xl[kFirst ? 4 * q + 3 : 0]};
+              tc::st4(my_ax + p.kx / 2 + 4 * q, w);
+            }
+          }
+      };
+      auto store_h = [&]() {                                       // A_h <- fp16(h)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = tc::pack_half2(h[16 * c + 2 * i], h[16 * c + 2 * i + 1]);
+          tc::st8(my_ah + 8 * c, v);
+        }
+      };
+
+      // FC + softmax of a step are computed right after its h' has been published, i.e. while the next step's
+      // r-gate MMAs run.  (Folding them into the gate phases instead was measured slower: the phases are bound by
+      // in-order issue latency with two warps per scheduler, not by MUFU throughput.)
+      float fc_part[kTcMaxClasses];
+      auto fc_accum = [&](int j0) {                                 // += h[j0..j0+7] * Wfc
+#pragma unroll
+        for (int j = j0; j < j0 + 8; ++j) {
+          const float4 wa = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8 + 4);
+          fc_part[0] = fmaf(h[j], wa.x, fc_part[0]); fc_part[1] = fmaf(h[j], wa.y, fc_part[1]);
+          fc_part[2] = fmaf(h[j], wa.z, fc_part[2]); fc_part[3] = fmaf(h[j], wa.w, fc_part[3]);
+          fc_part[4] = fmaf(h[j], wb.x, fc_part[4]); fc_part[5] = fmaf(h[j], wb.y, fc_part[5]);
+          fc_part[6] = fmaf(h[j], wb.z, fc_part[6]); fc_part[7] = fmaf(h[j], wb.w, fc_part[7]);
+        }
+      };
+      // add the two warpgroups' partial sums, softmax, write step t_done.  dynamic_rnn: zero output past the length
+      auto fc_finish = [&](int t_done, bool emit) {
+        if (wg == 1) {
+          const float g = emit ? 1.0f : 0.0f;
+          *reinterpret_cast<float4*>(sXch + row * 8) = make_float4(g * fc_part[0], g * fc_part[1], g * fc_part[2], g * fc_part[3]);
+          *reinterpret_cast<float4*>(sXch + row * 8 + 4) = make_float4(g * fc_part[4], g * fc_part[5], g * fc_part[6], g * fc_part[7]);
+          asm volatile("bar.arrive 1, 256;" ::: "memory");
+        } else {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (ok) {
+            float lg[8];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              lg[c] = (emit ? fc_part[c] : 0.0f) + sXch[row * 8 + c] + sFcb[c];
+              if (c < p.C) mx = fmaxf(mx, lg[c]);
+            }
+            float e[8], sum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              e[c] = c < p.C ? expf(lg[c] - mx) : 0.0f;
+              sum += e[c];
+            }
+            const float inv = 1.0f / sum;
+            float* pr = p.probs + (s * p.n + t_done) * p.C;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < p.C) pr[c] = e[c] * inv;
+            if (p.logits) {
+              float* lo = p.logits + (s * p.n + t_done) * p.C;
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                if (c < p.C) lo[c] = lg[c];
+            }
           }
         }
-    };
-    if (p.n > 0) {
+      };
+
+      // ---- prologue: A_x <- x_0, A_h <- fp16(h).  All MMAs of the previous tile have completed (its last
+      // commit was waited for by every thread), so both operand regions are free.
       load_x(0);
       store_x();
-    }
-
-    float fc_part[8];
-    bool fc_pending = false;
-    int fc_t = 0;
-    auto fc_finish = [&](int t_done) {                          // warpgroup 0: combine, softmax, write
-      if (wg == 0 && ok) {
-        float lg[8];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          lg[c] = fc_part[c] + sXch[row * 8 + c] + sFcb[c];
-          if (c < p.C) mx = fmaxf(mx, lg[c]);
-        }
-        float e[8], sum = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          e[c] = c < p.C ? expf(lg[c] - mx) : 0.0f;
-          sum += e[c];
-        }
-        float* pr = p.probs + (s * p.n + t_done) * p.C;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c < p.C) pr[c] = e[c] / sum;
-        if (p.logits) {
-          float* lo = p.logits + (s * p.n + t_done) * p.C;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c < p.C) lo[c] = lg[c];
-        }
-      }
-    };
-
-    for (int t = 0; t < p.n; ++t) {
-      // ---- A operand complete -> issue gate MMAs (+ the candidate's x part behind them)
+      store_h();
       tc::wait_st();
       tc::fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        tc::fence_after_sync();
-        // B descriptor of K-chunk k16 of the packed weights; rows 0..255 = gates, 256..383 = candidate
-        auto wdesc = [&](int k16, bool cand) {
-          return tc::smem_desc(sW_addr + (cand ? 32 * sbo : 0) + 256 * k16, 128, sbo);
-        };
-        const int nx = p.kx / 16, nxw = p.kxw / 16;
-        bool acc = false;
-        for (int k16 = 0; k16 < nx; ++k16, acc = true)                       // x_hi * Wx_hi
-          tc::mma_ts(tmem + colDg, tmem + colAx + 8 * k16, wdesc(k16, false), idesc_g, acc);
-        if (split) {
-          for (int k16 = 0; k16 < nx; ++k16)                                 // x_lo * Wx_hi
-            tc::mma_ts(tmem + colDg, tmem + colAxl + 8 * k16, wdesc(k16, false), idesc_g, true);
-          for (int k16 = 0; k16 < nx; ++k16)                                 // x_hi * Wx_lo
-            tc::mma_ts(tmem + colDg, tmem + colAx + 8 * k16, wdesc(nx + k16, false), idesc_g, true);
-        }
-        for (int k16 = 0; k16 < kHidden / 16; ++k16, acc = true)             // h * Wh
-          tc::mma_ts(tmem + colDg, tmem + colAh + 8 * k16, wdesc(nxw + k16, false), idesc_g, acc);
-        tc::commit(&bars[0]);
-        acc = false;
-        for (int k16 = 0; k16 < nx; ++k16, acc = true)
-          tc::mma_ts(tmem + colDc, tmem + colAx + 8 * k16, wdesc(k16, true), idesc_c, acc);
-        if (split) {
-          for (int k16 = 0; k16 < nx; ++k16)
-            tc::mma_ts(tmem + colDc, tmem + colAxl + 8 * k16, wdesc(k16, true), idesc_c, true);
-          for (int k16 = 0; k16 < nx; ++k16)
-            tc::mma_ts(tmem + colDc, tmem + colAx + 8 * k16, wdesc(nx + k16, true), idesc_c, true);
-        }
-      }
-      if (kLast && fc_pending) {                               // previous step's softmax, under the gate MMAs
-        fc_finish(fc_t);
-        fc_pending = false;
-      }
-      if (t + 1 < p.n) load_x(t + 1);                          // global loads in flight during the step
-      tc::mbar_wait(&bars[0], phase);
-      tc::fence_after_sync();
+      mbar_arrive(&bars[kBarAX]);
+      mbar_arrive(&bars[kBarAH]);
 
-      // ---- epilogue 1: r, u;  A_h <- fp16(r * h)
-      float u[kTcUnits];
+      for (int t = 0; t < p.n; ++t, ++it) {
+        const uint32_t par = it & 1;
+        const bool more = t + 1 < p.n;
+        // ---- r gate: keep fp16(r*h) in registers until the u-gate MMAs have finished reading A_h.
+        // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c goes through the MUFU chain.
+        uint32_t rh[kTcUnits / 2];
+        const bool tl = p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && t < 64;
+        if (tl) g_tc_timeline[t * 8 + 0] = clock64();
+        mbar_acquire(&bars[kBarR], par);
+        if (tl) g_tc_timeline[t * 8 + 1] = clock64();
+        {
+          uint32_t va[16], vb[16];
+          tc::ld16(tmem + lane_sel + colDr + u0, va);
+          tc::wait_ld();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t vr[16], vu[16];
-        tc::ld16(tmem + lane_sel + colDg + u0 + 16 * c, vr);
-        tc::ld16(tmem + lane_sel + colDg + kHidden + u0 + 16 * c, vu);
-        tc::wait_ld();
-        uint32_t packed[8];
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&cur)[16] = (c & 1) ? vb : va;
+            uint32_t (&nxt)[16] = (c & 1) ? va : vb;
+            if (c < 3) tc::ld16(tmem + lane_sel + colDr + u0 + 16 * (c + 1), nxt);
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const int j = 16 * c + i;
-          const float r0 = fast_sigmoid(__uint_as_float(vr[i]) + sBias[u0 + j]);
-          const float r1 = fast_sigmoid(__uint_as_float(vr[i + 1]) + sBias[u0 + j + 1]);
-          u[j] = fast_sigmoid(__uint_as_float(vu[i]) + sBias[kHidden + u0 + j]);
-          u[j + 1] = fast_sigmoid(__uint_as_float(vu[i + 1]) + sBias[kHidden + u0 + j + 1]);
-          packed[i / 2] = tc::pack_half2(r0 * h[j], r1 * h[j + 1]);
-        }
-        tc::st8(my_ah + 8 * c, packed);
-      }
-      tc::wait_st();
-      tc::fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        tc::fence_after_sync();
-        for (int k16 = 0; k16 < kHidden / 16; ++k16)
-          tc::mma_ts(tmem + colDc, tmem + colAh + 8 * k16, tc::smem_desc(sW_addr + 32 * sbo + 256 * (p.kxw / 16 + k16), 128, sbo),
-                     idesc_c, (p.kx > 0) || k16 > 0);
-        tc::commit(&bars[1]);
-      }
-      tc::mbar_wait(&bars[1], phase);
-      tc::fence_after_sync();
-      phase ^= 1;
-
-      // ---- epilogue 2: candidate, state update, outputs;  A_h <- fp16(h'),  A_x <- x_{t+1}
-      const bool live = t < len;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) fc_part[c] = 0.0f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t vc[16];
-        tc::ld16(tmem + lane_sel + colDc + u0 + 16 * c, vc);
-        tc::wait_ld();
-        uint32_t packed[8];
-        uint32_t ypacked[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const int j = 16 * c + i;
-          const float c0 = fast_tanh(__uint_as_float(vc[i]) + sBias[2 * kHidden + u0 + j]);
-          const float c1 = fast_tanh(__uint_as_float(vc[i + 1]) + sBias[2 * kHidden + u0 + j + 1]);
-          const float n0 = u[j] * h[j] + (1.0f - u[j]) * c0;
-          const float n1 = u[j + 1] * h[j + 1] + (1.0f - u[j + 1]) * c1;
-          h[j] = live ? n0 : h[j];
-          h[j + 1] = live ? n1 : h[j + 1];
-          const float y0 = live ? n0 : 0.0f, y1 = live ? n1 : 0.0f;       // dynamic_rnn: zero output past the length
-          packed[i / 2] = tc::pack_half2(h[j], h[j + 1]);
-          if (kLast) {
-            const float4 wa0 = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8);
-            const float4 wb0 = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8 + 4);
-            const float4 wa1 = *reinterpret_cast<const float4*>(sFcw + (u0 + j + 1) * 8);
-            const float4 wb1 = *reinterpret_cast<const float4*>(sFcw + (u0 + j + 1) * 8 + 4);
-            fc_part[0] = fmaf(y0, wa0.x, fc_part[0]); fc_part[1] = fmaf(y0, wa0.y, fc_part[1]);
-            fc_part[2] = fmaf(y0, wa0.z, fc_part[2]); fc_part[3] = fmaf(y0, wa0.w, fc_part[3]);
-            fc_part[4] = fmaf(y0, wb0.x, fc_part[4]); fc_part[5] = fmaf(y0, wb0.y, fc_part[5]);
-            fc_part[6] = fmaf(y0, wb0.z, fc_part[6]); fc_part[7] = fmaf(y0, wb0.w, fc_part[7]);
-            fc_part[0] = fmaf(y1, wa1.x, fc_part[0]); fc_part[1] = fmaf(y1, wa1.y, fc_part[1]);
-            fc_part[2] = fmaf(y1, wa1.z, fc_part[2]); fc_part[3] = fmaf(y1, wa1.w, fc_part[3]);
-            fc_part[4] = fmaf(y1, wb1.x, fc_part[4]); fc_part[5] = fmaf(y1, wb1.y, fc_part[5]);
-            fc_part[6] = fmaf(y1, wb1.z, fc_part[6]); fc_part[7] = fmaf(y1, wb1.w, fc_part[7]);
-          } else {
-            ypacked[i / 2] = tc::pack_half2(y0, y1);
+            for (int i = 0; i < 16; i += 2) {
+              const int j = 16 * c + i;
+              const float r0 = sigmoid_pre(__uint_as_float(cur[i]), bR[j]);
+              const float r1 = sigmoid_pre(__uint_as_float(cur[i + 1]), bR[j + 1]);
+              rh[j / 2] = tc::pack_half2(r0 * h[j], r1 * h[j + 1]);
+            }
+            if (c < 3) tc::wait_ld();
           }
         }
-        tc::st8(my_ah + 8 * c, packed);
-        if (!kLast && ok) {
-          uint4* dst = reinterpret_cast<uint4*>(p.y_f16 + (s * p.n + t) * static_cast<long>(kHidden) + u0 + 16 * c);
-          dst[0] = make_uint4(ypacked[0], ypacked[1], ypacked[2], ypacked[3]);
-          dst[1] = make_uint4(ypacked[4], ypacked[5], ypacked[6], ypacked[7]);
-        }
-      }
-      if (t + 1 < p.n) store_x();
-      if (kLast) {
-        if (wg == 1) {
-          *reinterpret_cast<float4*>(sXch + row * 8) = make_float4(fc_part[0], fc_part[1], fc_part[2], fc_part[3]);
-          *reinterpret_cast<float4*>(sXch + row * 8 + 4) = make_float4(fc_part[4], fc_part[5], fc_part[6], fc_part[7]);
-        }
-        fc_pending = true;
-        fc_t = t;
-      }
-    }
-    if (kLast && fc_pending) {
-      __syncthreads();
-      fc_finish(fc_t);
-      fc_pending = false;
-    }
-    if (ok) {
-      float4* dst = reinterpret_cast<float4*>(p.h_out + s * kHidden + u0);
+        if (tl) g_tc_timeline[t * 8 + 2] = clock64();
+        mbar_acquire(&bars[kBarU], par);
 #pragma unroll
-      for (int i = 0; i < kTcUnits / 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t v[8] = {rh[8 * c], rh[8 * c + 1], rh[8 * c + 2], rh[8 * c + 3],
+                                 rh[8 * c + 4], rh[8 * c + 5], rh[8 * c + 6], rh[8 * c + 7]};
+          tc::st8(my_ah + 8 * c, v);
+        }
+        tmem_publish(&bars[kBarARH]);
+        if (tl) g_tc_timeline[t * 8 + 3] = clock64();
+        if (more) load_x(t + 1);                                   // coalesced global loads in flight under the u gate
+        // ---- u gate (beside the candidate MMAs): activated in place, D_u keeps u until the update reads it
+        {
+          uint32_t va[16], vb[16];
+          tc::ld16(tmem + lane_sel + colDu + u0, va);
+          tc::wait_ld();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&cur)[16] = (c & 1) ? vb : va;
+            uint32_t (&nxt)[16] = (c & 1) ? va : vb;
+            if (c < 3) tc::ld16(tmem + lane_sel + colDu + u0 + 16 * (c + 1), nxt);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = __float_as_uint(sigmoid_pre(__uint_as_float(cur[i]), bU[16 * c + i]));
+            tc::st16(tmem + lane_sel + colDu + u0 + 16 * c, cur);
+            if (c < 3) tc::wait_ld();
+          }
+          tc::wait_st();
+        }
+        // ---- candidate and state update: only what the next step's MMAs wait for
+        if (tl) g_tc_timeline[t * 8 + 4] = clock64();
+        mbar_acquire(&bars[kBarC], par);
+        if (tl) g_tc_timeline[t * 8 + 5] = clock64();
+        if (more) {                                                // next step's x first: its r-gate MMAs run under this phase
+          store_x();
+          tmem_publish(&bars[kBarAX]);
+        }
+        const bool live = t < len;
+        {
+          uint32_t ca[16], cb[16], ua[16], ub[16];
+          tc::ld16(tmem + lane_sel + colDc + u0, ca);
+          tc::ld16(tmem + lane_sel + colDu + u0, ua);
+          tc::wait_ld();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&vc)[16] = (c & 1) ? cb : ca;
+            uint32_t (&vu)[16] = (c & 1) ? ub : ua;
+            if (c < 3) {
+              tc::ld16(tmem + lane_sel + colDc + u0 + 16 * (c + 1), (c & 1) ? ca : cb);
+              tc::ld16(tmem + lane_sel + colDu + u0 + 16 * (c + 1), (c & 1) ? ua : ub);
+            }
+            uint32_t packed[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const int j = 16 * c + i;
+              const float c0 = tanh_pre(__uint_as_float(vc[i]), bC[j]);
+              const float c1 = tanh_pre(__uint_as_float(vc[i + 1]), bC[j + 1]);
+              float n0 = fmaf(__uint_as_float(vu[i]), h[j] - c0, c0);          // u*h + (1-u)*c
+              float n1 = fmaf(__uint_as_float(vu[i + 1]), h[j + 1] - c1, c1);
+              if (!all_live) {                                     // dynamic_rnn: state carried past the length
+                n0 = live ? n0 : h[j];
+                n1 = live ? n1 : h[j + 1];
+              }
+              h[j] = n0;
+              h[j + 1] = n1;
+              packed[i / 2] = tc::pack_half2(n0, n1);
+            }
+            if (more) tc::st8(my_ah + 8 * c, packed);
+            if (c < 3) tc::wait_ld();
+          }
+        }
+        if (more) tmem_publish(&bars[kBarAH]);                     // releases the next step's r/u MMAs
+        if (tl) g_tc_timeline[t * 8 + 6] = clock64();
+        // ---- outputs of this step, in the shadow of the next step's r-gate MMAs.  dynamic_rnn: zero output past the length
+        const bool emit = all_live || live;
+        if (!kLast) {
+          {   // tiled hand-off (rows past S are written too: the scratch is padded to whole tiles)
+            uint4* dst = reinterpret_cast<uint4*>(p.y_f16) + ((tile * p.n + t) * 16 + 8 * wg) * kTcTile + row;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              uint4 v;
+              v.x = emit ? tc::pack_half2(h[8 * q], h[8 * q + 1]) : 0u;
+              v.y = emit ? tc::pack_half2(h[8 * q + 2], h[8 * q + 3]) : 0u;
+              v.z = emit ? tc::pack_half2(h[8 * q + 4], h[8 * q + 5]) : 0u;
+              v.w = emit ? tc::pack_half2(h[8 * q + 6], h[8 * q + 7]) : 0u;
+              dst[q * kTcTile] = v;
+            }
+          }
+        }
+        if (kLast) {                                               // in the shadow of the next step's r-gate MMAs
+#pragma unroll
+          for (int c = 0; c < kTcMaxClasses; ++c) fc_part[c] = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) fc_accum(8 * c);
+          fc_finish(t, emit);
+        }
+      }
+      if (p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x) g_tc_timeline[7] = clock64();
+      if (ok) {
+        float4* dst = reinterpret_cast<float4*>(p.h_out + s * kHidden + u0);
+#pragma unroll
+        for (int i = 0; i < kTcUnits / 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      }
     }
-    // the next tile's first barrier orders these TMEM stores / smem reads against its MMAs
-    __syncthreads();
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
 }
 
 static size_t gru_tc_smem_bytes(int ktot) {
-  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + kHidden * 8 + 8 + kTcTile * 8) + 2 * sizeof(uint64_t) + 16;
+  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + kHidden * 8 + 8 + kTcTile * 8) + kNumBars * sizeof(uint64_t) + 16;
 }
 
 // Pack one layer's TF kernels into the fp16 canonical [384, kxw+128] B operand: [Wx_hi | Wx_lo (split) | Wh].
@@ -419,7 +577,7 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     if (rc != KWS_OK) return rc;
   }
   const long ntiles = ceil_div(a.S, kTcTile);
-  const size_t per_buf = static_cast<size_t>(a.S) * a.n * kHidden;           // halves
+  const size_t per_buf = static_cast<size_t>(ntiles) * kTcTile * a.n * kHidden;     // halves (whole tiles)
   __half* seq = reinterpret_cast<__half*>(m->scratch_seq);
   for (int l = 0; l < L; ++l) {
     const bool last = l == L - 1;
@@ -430,6 +588,7 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     p.S = a.S;
     p.n = a.n;
     p.x_f32 = l == 0 ? a.x : nullptr;
+    p.x_tiled = l == 0 && a.x_tiled ? 1 : 0;
     p.x_f16 = l == 0 ? nullptr : seq + ((l - 1) & 1) * per_buf;
     p.y_f16 = last ? nullptr : seq + (l & 1) * per_buf;
     p.wpack = static_cast<const __half*>(m->layer[l].tc_wpack);
@@ -443,6 +602,7 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     p.C = m->cfg.num_classes;
     p.probs = a.probs;
     p.logits = a.logits;
+    p.timeline = g_tc_timeline_on;
     const size_t smem = gru_tc_smem_bytes(p.kxw + kHidden);
     const long blocks = ntiles < sm_count() ? ntiles : sm_count();
     const bool first = l == 0;
@@ -461,3 +621,17 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
 }
 
 }  // namespace kws
+
+// Debug: phase timeline (SM clock ticks) of the first tile of CTA 0 of the LAST tensor-core GRU launch:
+// per step t, [t*8 + k] = clock at {0 wait R, 1 got R, 2 r done, 3 r*h published, 4 u done, 5 got C, 6 h' published};
+// slot [7] = end of the tile.
+extern "C" int kws_debug_tc_timeline(int enable, long long* host_out, int count) {
+  using namespace kws;
+  clear_error();
+  g_tc_timeline_on = enable;
+  if (host_out && count > 0) {
+    if (count > 64 * 8) count = 64 * 8;
+    KWS_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_tc_timeline, sizeof(long long) * count));
+  }
+  return KWS_OK;
+}

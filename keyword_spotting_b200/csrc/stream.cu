@@ -269,7 +269,7 @@ extern "C" int kws_stream_create(kws_model* m, const kws_stream_config* cfg, kws
   }
   if (rc == KWS_OK) rc = dev_alloc(&st->silence, S, true);
   if (rc == KWS_OK) rc = dev_alloc(&st->nframes, S, true);
-  if (rc == KWS_OK) rc = dev_alloc(&st->mel, S * (mf ? mf : 1) * M, false);
+  if (rc == KWS_OK) rc = dev_alloc(&st->mel, mel_scratch_elems(st->S, mf, M), false);
   if (rc == KWS_OK) rc = dev_alloc(&st->probs, S * (mf ? mf : 1) * C, false);
   if (rc == KWS_OK) rc = dev_alloc(&st->tok, S * W * st->fpad, true);
   if (rc == KWS_OK) rc = dev_alloc(&st->slot_frames, S * W, true);
@@ -347,6 +347,7 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
   src.ld_head = kTailCap;
   src.head_len = st->tail_len[cur];
   const bool fused = frontend_can_fuse_pre(chunk_len, kTailCap);
+  const bool tiled = mel_can_tile(m);
   if (fused) {
     // one pass over the chunk: VAD + tail carry + frame count + framing/FFT/mel
     FrontendPre pre;
@@ -355,7 +356,7 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
     pre.len_next = st->tail_len[nxt];
     pre.silence = st->silence;
     pre.nframes_out = st->nframes;
-    int rc = launch_frontend(m, src, S, n_step, nullptr, st->mel, cs, &pre);
+    int rc = launch_frontend(m, src, S, n_step, nullptr, st->mel, cs, &pre, tiled);
     if (rc != KWS_OK) return rc;
   } else {
     stream_pre_kernel<<<static_cast<unsigned>(ceil_div(S * 32, 256)), 256, 0, cs>>>(
@@ -366,12 +367,13 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
 
   if (n_step > 0) {
     if (!fused) {
-      int rc = launch_frontend(m, src, S, n_step, st->nframes, st->mel, cs);
+      int rc = launch_frontend(m, src, S, n_step, st->nframes, st->mel, cs, nullptr, tiled);
       if (rc != KWS_OK) return rc;
     }
     int rc = KWS_OK;
     GruArgs a;
     a.x = st->mel;
+    a.x_tiled = tiled;
     a.S = S;
     a.n = n_step;
     a.seq_len = st->nframes;

@@ -16,7 +16,7 @@ TOL_CONTRACT = 1e-3
 TOL_FP32 = 1e-4
 
 
-TOL_TC_LOGIC = 1e-4       # tensor-core kernel vs the oracle run with the SAME operand rounding (fp16 operands);
+TOL_TC_LOGIC = 2e-4       # tensor-core kernel vs the oracle run with the SAME operand rounding (fp16 operands);
                           # what is left is accumulation order and the ex2/rcp.approx gate functions (measured 3.3e-5)
 
 

@@ -37,6 +37,9 @@ METRIC = "streamed audio-sec/sec, 2L GRU-128 KWS"
 UNIT = "audio-s/s"
 # algorithmic work: GRU 325,632 + FC 1,536 FLOP per frame
 GRU_FLOP_PER_FRAME = 2 * (40 * 384 + 128 * 384 + 128 * 384 + 128 * 384) + 2 * 128 * 6
+# front-end kernel, compulsory bytes per stream-chunk: 4800 int16 in, carried tail 320 samples read + written,
+# 30 x 40 fp32 mel out, VAD flag + frame count + tail length
+FE_BYTES_PER_STREAM_CHUNK = CHUNK * 2 + 2 * 320 * 2 + FRAMES * 40 * 4 + 9
 
 
 def parse_args():
@@ -49,6 +52,10 @@ def parse_args():
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="recurrent kernel: tc = tcgen05 fp16 operands / fp32 accumulate (default), fp32 = exact FFMA path")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--waves", type=int, default=8, help="e2e: the streams of a GPU are served in this many waves "
+                    "(independent stream objects on their own CUDA streams) so copies overlap compute and a chunk's "
+                    "latency is one wave's, not the whole batch's")
+    ap.add_argument("--depth", type=int, default=2, help="e2e: waves in flight")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-streams", type=int, default=0, help="CPU sample: streams (default 64 per host core)")
     ap.add_argument("--cpu-chunks", type=int, default=0, help="CPU sample: chunks per step (default: calibrated)")
@@ -151,7 +158,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -264,9 +271,8 @@ def run_ours(args, rank, world, local_rank):
         step_dev(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                              # 50 ms samples over every timed region below
     total_ms, per_step = timed_loop(torch, step_dev, args.steps, stream, barrier)
-    clocks = sampler.stop() if rank == 0 else None
     total_ms_max = sharding.reduce_max_scalar(total_ms, device)
     ms_per_step = total_ms_max / args.steps
     value = world * S * AUDIO_S_PER_CHUNK * args.steps / (total_ms_max * 1e-3)
@@ -293,45 +299,105 @@ def run_ours(args, rank, world, local_rank):
     gru_ms, _ = timed_loop(torch, gru_only, k_iters, stream, lambda: None)
     fe_ms, _ = timed_loop(torch, fe_only, k_iters, stream, lambda: None)
     gru_launch_ms = gru_ms / k_iters / cfg.num_layers
+    fe_launch_ms = fe_ms / k_iters
     peaks = load_peaks()
     flop_per_launch = S * FRAMES * GRU_FLOP_PER_FRAME / cfg.num_layers
     achieved_tf = flop_per_launch / (gru_launch_ms * 1e-3) / 1e12
     kname = "gru_tc_kernel" if args.precision == "tc" else "gru_layer_kernel"
-    roofline = dict(kernel=kname, bound="tensor", achieved=achieved_tf, peak=peaks["bf16_sustained"],
-                    unit="TFLOP/s", frac=achieved_tf / peaks["bf16_sustained"], traffic=None,
+    roof_gru = dict(kernel=kname, bound="tensor", achieved=achieved_tf, peak=peaks["bf16_sustained"],
+                    unit="TFLOP/s", frac=achieved_tf / peaks["bf16_sustained"], traffic=None, launch_ms=gru_launch_ms,
                     peak_source=peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                     note=("tcgen05 kind::f16 (fp16 operands, fp32 accumulate); " if args.precision == "tc" else
                           "exact fp32 FFMA kernel measured against the tensor-pipe peak; ") +
                          "algorithmic FLOP = 327,168 per frame (GRU 325,632 + FC 1,536), one launch per layer")
+    fe_gbs = S * FE_BYTES_PER_STREAM_CHUNK / (fe_launch_ms * 1e-3) / 1e9
+    roof_fe = dict(kernel="frontend_kernel", bound="hbm", achieved=fe_gbs, peak=peaks["hbm"], unit="GB/s",
+                   frac=fe_gbs / peaks["hbm"], traffic=None, launch_ms=fe_launch_ms,
+                   peak_source=peaks["source"] + ", copy bandwidth",
+                   note="algorithmic bytes = %d per stream-chunk (int16 PCM in, carried tail r+w, fp32 mel out, flags); "
+                        "one launch per step; timed here on a 5120-sample input without the fused VAD/tail work" % FE_BYTES_PER_STREAM_CHUNK)
+    # the roofline of the dominant kernel (largest launch time); the other one alongside
+    roofline, roofline_other = (roof_fe, roof_gru) if fe_launch_ms >= gru_launch_ms else (roof_gru, roof_fe)
     del pcm_full, mel, probs, st
 
-    # ---- end to end through the host-buffer C-ABI call
+    # ---- end to end through the host-buffer C-ABI call, served in waves
     e2e = None
+    latency = None
     if not args.no_e2e:
+        det.close()                                  # the full-batch server is not needed any more
+        del chunks[2:]
+        W = max(1, min(args.waves, S // 128))
+        Sw = S // W
+        assert Sw * W == S, "--streams must be divisible by --waves"
         n_host = 2
-        host = [torch.empty((S, CHUNK), dtype=torch.int16).pin_memory() for _ in range(n_host)]
-        for b in range(n_host):
-            host[b].copy_(chunks[b])
-        host_trig = torch.zeros(S, dtype=torch.int32).pin_memory()
-        det.reset()
+        host = [[torch.empty((Sw, CHUNK), dtype=torch.int16).pin_memory() for _ in range(n_host)] for _ in range(W)]
+        for w in range(W):
+            for b in range(n_host):
+                host[w][b].copy_(chunks[b][w * Sw:(w + 1) * Sw])
+        host_trig = [torch.zeros(Sw, dtype=torch.int32).pin_memory() for _ in range(W)]
+        dets = [StreamingDetector(model, Sw) for _ in range(W)]
+        wstreams = [torch.cuda.Stream(device=device) for _ in range(W)]
+        lat = []
 
-        def step_e2e(i):
-            det.step_host(host[i % n_host], host_trig)
+        def run_e2e(n_steps, record):
+            """n_steps chunks for every stream: wave by wave, at most --depth waves in flight.  A wave's latency runs
+            from the moment its chunk is handed to the C-ABI call (host clock) to its trigger flags being back on the host."""
+            from collections import deque
+            inflight = deque()
+            for k in range(n_steps):
+                for w in range(W):
+                    if len(inflight) >= args.depth:
+                        t_enq, ev = inflight.popleft()
+                        ev.synchronize()
+                        if record:
+                            lat.append((time.perf_counter() - t_enq) * 1e3)
+                    t_enq = time.perf_counter()
+                    with torch.cuda.stream(wstreams[w]):
+                        dets[w].step_host(host[w][k % n_host], host_trig[w])
+                        ev = torch.cuda.Event()
+                        ev.record(wstreams[w])
+                    inflight.append((t_enq, ev))
+            while inflight:
+                t_enq, ev = inflight.popleft()
+                ev.synchronize()
+                if record:
+                    lat.append((time.perf_counter() - t_enq) * 1e3)
 
-        for i in range(3):
-            step_e2e(i)
+        run_e2e(3, False)
         torch.cuda.synchronize()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        e2e_ms, _ = timed_loop(torch, step_e2e, args.steps, stream, barrier)
+        ev0.record(stream)
+        for ws in wstreams:
+            ws.wait_stream(stream)
+        run_e2e(args.steps, True)
+        for ws in wstreams:
+            stream.wait_stream(ws)
+        ev1.record(stream)
+        torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        e2e_ms = ev0.elapsed_time(ev1)
         e2e_ms_max = sharding.reduce_max_scalar(max(e2e_ms, 0.0), device)
         e2e = dict(value=world * S * AUDIO_S_PER_CHUNK * args.steps / (e2e_ms_max * 1e-3), unit=UNIT,
                    h2d_bytes_per_step=S * CHUNK * 2, d2h_bytes_per_step=S * 4, ms_per_step=e2e_ms_max / args.steps,
-                   wall_ms_per_step=wall_ms / args.steps,
-                   note="pinned host int16 PCM -> H2D -> kws_stream_step -> D2H trigger flags, every step, copies "
-                        "double-buffered against compute inside the timed region")
-        trig_total += int(host_trig.sum())
+                   wall_ms_per_step=wall_ms / args.steps, waves=W, depth=args.depth,
+                   note="pinned host int16 PCM -> H2D -> kws_stream_step -> D2H trigger flags for every stream every step, "
+                        "through kws_stream_step_host; the streams are served as %d waves of %d (one stream object and CUDA "
+                        "stream each), %d in flight, so H2D of one wave overlaps the kernels of another; bound by the host link "
+                        "(%.1f GB/s achieved)" % (W, Sw, args.depth, S * CHUNK * 2 / (e2e_ms_max / args.steps * 1e-3) / 1e9))
+        lat.sort()
+        latency = dict(unit="ms", p50=lat[len(lat) // 2], p99=lat[min(len(lat) - 1, int(0.99 * len(lat)))], max=lat[-1],
+                       samples=len(lat),
+                       definition="host clock from handing a wave's 300 ms chunk (pinned host memory) to kws_stream_step_host "
+                                  "until its trigger flags are back on the host, measured inside the e2e timed region "
+                                  "(includes queueing behind the %d wave(s) in flight)" % (args.depth - 1))
+        trig_total += int(sum(int(t.sum()) for t in host_trig))
+        for d in dets:
+            d.close()
         del host
+    clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
         dist.all_reduce(trig_total)                  # the final result gather (NCCL), off the hot path
@@ -348,9 +414,13 @@ def run_ours(args, rank, world, local_rank):
                                          "state and VAD reset, 300 ms chunks, 2L GRU-128 n_mel=40 6 classes" % S,
                                 streams_per_gpu=S, chunk_samples=CHUNK, frames_per_chunk=FRAMES, sharding="streams/dp%d" % world,
                                 l2_policy="inputs larger than L2: %d rotating 1.26 GB PCM buffers" % n_buf),
-                    realtime_streams=value / 1.0, chunk_latency_ms_p99=per_sorted[min(len(per_sorted) - 1, int(0.99 * len(per_sorted)))],
+                    realtime_streams=value / 1.0,
+                    realtime_streams_e2e=(e2e["value"] if e2e else None),
+                    chunk_latency_ms_p99=(latency["p99"] if latency else None), chunk_latency=latency,
+                    full_batch_step_ms_p99=per_sorted[min(len(per_sorted) - 1, int(0.99 * len(per_sorted)))],
                     kernels_ms=dict(frontend=fe_ms / k_iters, gru_2_layers=gru_ms / k_iters, step_total=ms_per_step),
-                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=5 * args.steps, clocks=clocks,
+                    roofline=roofline, roofline_other=[roofline_other], cpu_baseline=cpu, e2e=e2e,
+                    gpu_launches=4 * args.steps, clocks=clocks,
                     triggers=int(trig_total.item()))
         print(json.dumps(line), flush=True)
     det.close()

@@ -231,9 +231,7 @@ extern "C" int kws_model_reserve(kws_model* m, int64_t max_streams, int32_t max_
   m->cap_streams = 0;
   m->cap_frames = 0;
   const size_t mel_elems = mel_scratch_elems(S, n, m->cfg.n_mel);
-  const size_t tiles = static_cast<size_t>(ceil_div(S, 128) * 2);
-  const int nbuf = m->cfg.num_layers > 2 ? 2 : 1;
-  const size_t seq_elems = tiles * n * kHidden * 64 * nbuf;
+  const size_t seq_elems = seq_scratch_elems(S, n, m->cfg.num_layers);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->scratch_mel), sizeof(float) * (mel_elems ? mel_elems : 1));
   if (e == cudaSuccess && m->cfg.num_layers > 1)
     e = cudaMalloc(reinterpret_cast<void**>(&m->scratch_seq), sizeof(float) * (seq_elems ? seq_elems : 1));

@@ -138,7 +138,12 @@ struct GruArgs {
   float* state_out = nullptr;             // [layers, S, H]
   float* probs = nullptr;                 // [S, n, C]
   float* logits = nullptr;                // [S, n, C] or null
+  float* seq_scratch = nullptr;           // inter-layer hand-off of seq_scratch_elems() floats; null -> the model's own
 };
+inline size_t seq_scratch_elems(int64_t S, int32_t n, int num_layers) {
+  if (num_layers < 2) return 0;
+  return static_cast<size_t>(ceil_div(S, 128) * 2) * (n > 0 ? n : 1) * kHidden * 64 * (num_layers > 2 ? 2 : 1);
+}
 int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st);        // dispatches on m->precision
 int launch_gru_fp32(kws_model* m, const GruArgs& a, cudaStream_t st);   // gru.cu   (exact fp32 FFMA)
 int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st);     // gru_tc.cu (tcgen05, fp16 operands)

@@ -321,10 +321,11 @@ int launch_gru_fp32(kws_model* m, const GruArgs& a, cudaStream_t st) {
     }
     return KWS_OK;
   }
-  if (L > 1) {
+  if (L > 1 && !a.seq_scratch) {
     const int rc = kws_model_reserve(m, a.S, a.n);
     if (rc != KWS_OK) return rc;
   }
+  float* seq = a.seq_scratch ? a.seq_scratch : m->scratch_seq;
   const long per_buf = ntiles * a.n * static_cast<long>(kH) * kTs;
   for (int l = 0; l < L; ++l) {
     const bool last = l == L - 1;
@@ -333,8 +334,8 @@ int launch_gru_fp32(kws_model* m, const GruArgs& a, cudaStream_t st) {
     p.S = a.S;
     p.n = a.n;
     p.x_rowmajor = l == 0 ? a.x : nullptr;
-    p.x_tiled = l == 0 ? nullptr : m->scratch_seq + ((l - 1) & 1) * per_buf;
-    p.y_tiled = last ? nullptr : m->scratch_seq + (l & 1) * per_buf;
+    p.x_tiled = l == 0 ? nullptr : seq + ((l - 1) & 1) * per_buf;
+    p.y_tiled = last ? nullptr : seq + (l & 1) * per_buf;
     p.wg = m->layer[l].gates_kernel;
     p.bg = m->layer[l].gates_bias;
     p.wc = m->layer[l].cand_kernel;

@@ -572,13 +572,13 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
       KWS_CUDA_OK(cudaMemcpyAsync(a.state_out, a.state_in, sizeof(float) * L * a.S * kHidden, cudaMemcpyDeviceToDevice, st));
     return KWS_OK;
   }
-  if (L > 1) {
+  if (L > 1 && !a.seq_scratch) {
     const int rc = kws_model_reserve(m, a.S, a.n);
     if (rc != KWS_OK) return rc;
   }
   const long ntiles = ceil_div(a.S, kTcTile);
   const size_t per_buf = static_cast<size_t>(ntiles) * kTcTile * a.n * kHidden;     // halves (whole tiles)
-  __half* seq = reinterpret_cast<__half*>(m->scratch_seq);
+  __half* seq = reinterpret_cast<__half*>(a.seq_scratch ? a.seq_scratch : m->scratch_seq);
   for (int l = 0; l < L; ++l) {
     const bool last = l == L - 1;
     GruTcParams p;

@@ -32,6 +32,7 @@ struct kws_stream {
   unsigned char* silence = nullptr; // [S] 1 = VAD said silence for the current chunk
   int32_t* nframes = nullptr;       // [S]
   float* mel = nullptr;             // [S, max_frames, M]
+  float* seq = nullptr;             // inter-layer hand-off, private so that stream objects can run concurrently
   float* probs = nullptr;           // [S, max_frames, C]
   signed char* tok = nullptr;       // [S, W, fpad]
   unsigned char* slot_frames = nullptr;  // [S, W]
@@ -220,6 +221,7 @@ static void free_stream(kws_stream* st) {
   cudaFree(st->silence);
   cudaFree(st->nframes);
   cudaFree(st->mel);
+  cudaFree(st->seq);
   cudaFree(st->probs);
   cudaFree(st->tok);
   cudaFree(st->slot_frames);
@@ -276,7 +278,7 @@ extern "C" int kws_stream_create(kws_model* m, const kws_stream_config* cfg, kws
   if (rc == KWS_OK) rc = dev_alloc(&st->win_head, S, true);
   if (rc == KWS_OK) rc = dev_alloc(&st->win_n, S, true);
   if (rc == KWS_OK) rc = dev_alloc(&st->trigger, S, true);
-  if (rc == KWS_OK && mf > 0) rc = kws_model_reserve(m, st->S, mf);
+  if (rc == KWS_OK && mf > 0 && L > 1) rc = dev_alloc(&st->seq, seq_scratch_elems(st->S, mf, L), false);
   if (rc != KWS_OK) {
     free_stream(st);
     return rc;
@@ -374,6 +376,7 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
     GruArgs a;
     a.x = st->mel;
     a.x_tiled = tiled;
+    a.seq_scratch = st->seq;
     a.S = S;
     a.n = n_step;
     a.seq_len = st->nframes;

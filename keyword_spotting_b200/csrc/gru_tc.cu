@@ -14,9 +14,10 @@
 //     needed.  TMEM map (512 columns): D_r 0..127, D_u 128..255, D_cand 256..383, A_x, A_h;
 //   * the input projection is not a separate GEMM: x_t W[0:in] is accumulated into the same TMEM tile as
 //     h W[in:], and it is issued a phase early so it never sits on the recurrent critical path;
-//   * warp-specialised: warps 0-7 (two warpgroups that split the 128 hidden units) run the gate algebra from
-//     TMEM; warp 8 only issues MMAs.  Everything is handed over with mbarriers (tcgen05.commit one way,
-//     256-thread arrivals the other) -- no CTA-wide barrier inside the time loop.  Per step:
+//   * warp-specialised: warps 0-15 run the gate algebra from TMEM (warp w: the 32 streams of TMEM lane quarter w%4,
+//     hidden units [32*(w/4), +32) -- four warps per scheduler hide the MUFU / TMEM-load latencies); warp 16 only
+//     issues MMAs.  Everything is handed over with mbarriers (tcgen05.commit one way,
+//     512-thread arrivals the other) -- no CTA-wide barrier inside the time loop.  Per step:
 //         MMA warp                                   epilogue threads
 //         r-gate x-part             <- A_x ready     ...
 //         r-gate h-part -> commit R <- A_h ready
@@ -42,10 +43,12 @@
 namespace kws {
 
 constexpr int kTcTile = 128;
-constexpr int kTcEpiThreads = 256;        // warps 0-7: gate algebra
-constexpr int kTcThreads = 384;           // + warpgroup 2: warp 8 issues the MMAs (warps 9-11 only donate registers)
-constexpr int kTcUnits = kHidden / 2;     // hidden units per epilogue thread (warpgroup split)
+constexpr int kTcEpiWarps = 16;           // warps 0-15: gate algebra.  Warp w owns TMEM lanes 32*(w%4).. (its 32 streams)
+constexpr int kTcEpiThreads = 32 * kTcEpiWarps;   //   and the 32 hidden units [32*(w/4), +32) of those streams
+constexpr int kTcThreads = kTcEpiThreads + 128;   // + warpgroup 4: warp 16 issues the MMAs (warps 17-19 only donate registers)
+constexpr int kTcUnits = 32;              // hidden units per gate thread
 constexpr int kTcMaxClasses = 8;          // FC columns kept per thread
+
 
 struct GruTcParams {
   int kx;                      // x width padded to a multiple of 16
@@ -113,6 +116,7 @@ static int g_tc_timeline_on = 0;
 enum { kBarAX = 0, kBarAH, kBarARH, kBarR, kBarU, kBarC, kNumBars };
 
 // kFirst: layer 0 -- x is fp32 (mel) and its projection uses the 3-term split.
+// kFirst: layer 0 -- x is fp32 (mel) and its projection uses the 3-term split.
 template <bool kLast, bool kFirst>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gru_tc_kernel(const GruTcParams p) {
@@ -122,13 +126,14 @@ gru_tc_kernel(const GruTcParams p) {
   float* sBias = reinterpret_cast<float*>(smem + static_cast<size_t>(384) * ktot * 2);   // [384] pre-scaled
   float* sFcw = sBias + 384;                                                        // [128][8]
   float* sFcb = sFcw + kHidden * kTcMaxClasses;                                     // [8]
-  float* sXch = sFcb + kTcMaxClasses;                                               // [128][8] FC partials of warpgroup 1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + kTcTile * kTcMaxClasses);     // [kNumBars]
+  float* sXch = sFcb + kTcMaxClasses;                                               // [3][128][8] FC partials of unit blocks 1..3
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 3 * kTcTile * kTcMaxClasses); // [kNumBars]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kMmaWarp = kTcEpiWarps;
 
-  if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) tc::tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
     tc::mbar_init(&bars[kBarAX], kTcEpiThreads);
     tc::mbar_init(&bars[kBarAH], kTcEpiThreads);
@@ -164,14 +169,14 @@ gru_tc_kernel(const GruTcParams p) {
   const uint32_t colAh = colAx + p.kxw / 2;
   const long ntiles = (p.S + kTcTile - 1) / kTcTile;
 
-  if (warp >= 8) {
-    // =========================================================== MMA issuer (one elected lane of warp 8)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    if (warp == 8) {
+  if (warp >= kMmaWarp) {
+    // =========================================================== MMA issuer (one elected lane of warp 16)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == kMmaWarp) {
       const uint32_t sbo = static_cast<uint32_t>(ktot / 8) * 128;
       const uint32_t idesc128 = tc::idesc_f16(128, 128);
       const int nx = p.kx / 16, nxw = p.kxw / 16;
-      const bool lead = (tid & 31) == 0;
+      const bool lead = lane == 0;
       // All operand addresses are computed warp-uniformly (they live in uniform registers); only the MMA itself is
       // predicated on the elected lane.  B descriptor of K-chunk k16 for the weight rows starting at row0 =
       // base + ((row0/8)*sbo + 256*k16)/16 added to the 14-bit start-address field (shared memory < 256 KB: no carry).
@@ -180,18 +185,21 @@ gru_tc_kernel(const GruTcParams p) {
       // x-part of a product into D columns `dcol` (overwrites D), weight rows starting at 128*rblk
       auto issue_x = [&](uint32_t dcol, int rblk) {
         const uint64_t wrow = wbase + rblk * row_step;
+#pragma unroll 1
         for (int k16 = 0; k16 < nx; ++k16)                                   // x_hi * Wx_hi
           if (lead) tc::mma_ts(tmem + dcol, tmem + colAx + 8 * k16, wrow + 16 * k16, idesc128, k16 > 0);
         if (split) {
+#pragma unroll 1
           for (int k16 = 0; k16 < nx; ++k16)                                 // x_lo * Wx_hi
             if (lead) tc::mma_ts(tmem + dcol, tmem + colAxl + 8 * k16, wrow + 16 * k16, idesc128, true);
+#pragma unroll 1
           for (int k16 = 0; k16 < nx; ++k16)                                 // x_hi * Wx_lo
             if (lead) tc::mma_ts(tmem + dcol, tmem + colAx + 8 * k16, wrow + 16 * (nx + k16), idesc128, true);
         }
       };
       auto issue_h = [&](uint32_t dcol, int rblk) {                          // += A_h * Wh[128*rblk .. +127]
         const uint64_t wrow = wbase + rblk * row_step + 16 * nxw;
-#pragma unroll
+#pragma unroll 1
         for (int k16 = 0; k16 < kHidden / 16; ++k16)
           if (lead) tc::mma_ts(tmem + dcol, tmem + colAh + 8 * k16, wrow + 16 * k16, idesc128, true);
       };
@@ -211,23 +219,22 @@ gru_tc_kernel(const GruTcParams p) {
           mbar_acquire(&bars[kBarARH], par);
           issue_h(colDc, 2);
           if (lead) tc::commit(&bars[kBarC]);
-          __syncwarp();
         }
       }
     }
   } else {
-    // =========================================================== gate algebra (256 threads, one stream each x 64 units)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");      // launched at 168: 128 x (168-72) released = 256 x (216-168) acquired
-    const int wg = tid >> 7, row = tid & 127;
-    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t my_ah = tmem + lane_sel + colAh + 32 * wg;      // this thread's 64 units = 32 columns
-    const int xq = p.kx / 16;                                       // st4 groups of x per warpgroup
-    const uint32_t my_ax = tmem + lane_sel + colAx + (p.kx / 4) * wg;
-    const int u0 = 64 * wg;                                         // first hidden unit of this thread
+    // =========================================================== gate algebra (512 threads: one stream x 32 units each)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");      // launched at 96: 128 x (96-32) released = 512 x (112-96) acquired
+    const int quarter = warp & 3, ublk = warp >> 2;
+    const int row = 32 * quarter + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(32 * quarter) << 16;
+    const int u0 = kTcUnits * ublk;                                 // first hidden unit of this thread
+    const uint32_t my_ah = tmem + lane_sel + colAh + 16 * ublk;     // 32 units = 16 columns
+    const int xq = p.kx / 16;                                       // layer 0: float4 chunks of x per thread
+    const uint32_t my_ax = tmem + lane_sel + colAx + (p.kx / 8) * ublk;
     const float* bR = sBias + u0;
     const float* bU = sBias + kHidden + u0;
     const float* bC = sBias + 2 * kHidden + u0;
-    const bool x_vec = kFirst && (p.in_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x_f32) & 15) == 0;
     uint32_t it = 0;
 
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -247,118 +254,103 @@ gru_tc_kernel(const GruTcParams p) {
           h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
         }
       }
-      uint32_t xr[32];                                             // x_t of this thread's half of the row, packed fp16 pairs
-      uint32_t xl[kFirst ? 32 : 1];                                // residuals x - fp16(x) (split only)
+      // x_t of this thread: K elements [ (kx/4)*ublk, +kx/4 ) of the row, as packed fp16 pairs (hi, and lo when split)
+      uint32_t xr[16];
+      uint32_t xl[kFirst ? 16 : 1];
       auto load_x = [&](int t) {
         if (!kFirst) {
           // chunk q of stream `row` sits at ((tile*n + t)*16 + q)*128 + row: a warp reads 512 contiguous bytes
-          const uint4* src = reinterpret_cast<const uint4*>(p.x_f16) + ((tile * p.n + t) * 16 + 8 * wg) * kTcTile + row;
+          const uint4* src = reinterpret_cast<const uint4*>(p.x_f16) + ((tile * p.n + t) * 16 + 4 * ublk) * kTcTile + row;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             const uint4 v = __ldg(src + q * kTcTile);
             xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
           }
         } else {
-          const float* src = p.x_f32 + (sr * p.n + t) * static_cast<long>(p.in_dim);
-          const int k0 = (p.kx / 2) * wg;
+          const int k0 = (p.kx / 4) * ublk;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             if (q < xq) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = 0.0f;
-              const int k = k0 + 8 * q;
-              if (p.x_tiled) {
-                // float4 chunk c of stream `row` sits at ((tile*n + t)*Q + c)*128 + row, Q = in_dim/4
-                const float4* src4 = reinterpret_cast<const float4*>(p.x_f32) + (tile * p.n + t) * static_cast<long>(p.in_dim / 4) * kTcTile + row;
-                if (k < p.in_dim) {
-                  const float4 v = __ldg(src4 + (k / 4) * kTcTile);
-                  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-                }
-                if (k + 4 < p.in_dim) {
-                  const float4 v = __ldg(src4 + (k / 4 + 1) * kTcTile);
-                  f[4] = v.x; f[5] = v.y; f[6] = v.z; f[7] = v.w;
-                }
-              } else if (ok) {
-                if (x_vec) {
-                  if (k < p.in_dim) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
-                    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-                  }
-                  if (k + 4 < p.in_dim) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + k + 4));
-                    f[4] = v.x; f[5] = v.y; f[6] = v.z; f[7] = v.w;
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    if (k + i < p.in_dim) f[i] = __ldg(src + k + i);
+              const int k = k0 + 4 * q;
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k < p.in_dim) {
+                if (p.x_tiled) {
+                  // float4 chunk c of stream `row` sits at ((tile*n + t)*Q + c)*128 + row, Q = in_dim/4
+                  v = __ldg(reinterpret_cast<const float4*>(p.x_f32) +
+                            ((tile * p.n + t) * static_cast<long>(p.in_dim / 4) + (k >> 2)) * kTcTile + row);
+                } else if (ok) {
+                  const float* src = p.x_f32 + (sr * p.n + t) * static_cast<long>(p.in_dim) + k;
+                  v.x = __ldg(src);
+                  if (k + 1 < p.in_dim) v.y = __ldg(src + 1);
+                  if (k + 2 < p.in_dim) v.z = __ldg(src + 2);
+                  if (k + 3 < p.in_dim) v.w = __ldg(src + 3);
                 }
               }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __half2 hi = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-                const float2 back = __half22float2(hi);
-                xr[4 * q + i] = *reinterpret_cast<const uint32_t*>(&hi);
-                xl[kFirst ? 4 * q + i : 0] = tc::pack_half2(f[2 * i] - back.x, f[2 * i + 1] - back.y);
-              }
+              const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+              const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+              xr[2 * q] = *reinterpret_cast<const uint32_t*>(&h0);
+              xr[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+              xl[kFirst ? 2 * q : 0] = tc::pack_half2(v.x - b0.x, v.y - b0.y);
+              xl[kFirst ? 2 * q + 1 : 0] = tc::pack_half2(v.z - b1.x, v.w - b1.y);
             }
           }
         }
       };
       auto store_x = [&]() {
+        if (!kFirst) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (q < xq) {
+          for (int q = 0; q < 4; ++q) {
             const uint32_t v[4] = {xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]};
             tc::st4(my_ax + 4 * q, v);
-            if (split) {
-              const uint32_t w[4] = {xl[kFirst ? 4 * q : 0], xl[kFirst ? 4 * q + 1 : 0], xl[kFirst ? 4 * q + 2 : 0],
-                                     xl[kFirst ? 4 * q + 3 : 0]};
-              tc::st4(my_ax + p.kx / 2 + 4 * q, w);
-            }
           }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < xq) {
+              tc::st2(my_ax + 2 * q, xr[2 * q], xr[2 * q + 1]);
+              if (split) tc::st2(my_ax + p.kx / 2 + 2 * q, xl[kFirst ? 2 * q : 0], xl[kFirst ? 2 * q + 1 : 0]);
+            }
+        }
       };
       auto store_h = [&]() {                                       // A_h <- fp16(h)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = tc::pack_half2(h[16 * c + 2 * i], h[16 * c + 2 * i + 1]);
           tc::st8(my_ah + 8 * c, v);
         }
       };
-
       // FC + softmax of a step are computed right after its h' has been published, i.e. while the next step's
-      // r-gate MMAs run.  (Folding them into the gate phases instead was measured slower: the phases are bound by
-      // in-order issue latency with two warps per scheduler, not by MUFU throughput.)
-      float fc_part[kTcMaxClasses];
-      auto fc_accum = [&](int j0) {                                 // += h[j0..j0+7] * Wfc
-#pragma unroll
-        for (int j = j0; j < j0 + 8; ++j) {
-          const float4 wa = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8);
-          const float4 wb = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8 + 4);
-          fc_part[0] = fmaf(h[j], wa.x, fc_part[0]); fc_part[1] = fmaf(h[j], wa.y, fc_part[1]);
-          fc_part[2] = fmaf(h[j], wa.z, fc_part[2]); fc_part[3] = fmaf(h[j], wa.w, fc_part[3]);
-          fc_part[4] = fmaf(h[j], wb.x, fc_part[4]); fc_part[5] = fmaf(h[j], wb.y, fc_part[5]);
-          fc_part[6] = fmaf(h[j], wb.z, fc_part[6]); fc_part[7] = fmaf(h[j], wb.w, fc_part[7]);
-        }
-      };
-      // add the two warpgroups' partial sums, softmax, write step t_done.  dynamic_rnn: zero output past the length
+      // r-gate MMAs run: 32 units per thread, partial sums of unit blocks 1..3 handed to block 0 through smem.
       auto fc_finish = [&](int t_done, bool emit) {
-        if (wg == 1) {
-          const float g = emit ? 1.0f : 0.0f;
-          *reinterpret_cast<float4*>(sXch + row * 8) = make_float4(g * fc_part[0], g * fc_part[1], g * fc_part[2], g * fc_part[3]);
-          *reinterpret_cast<float4*>(sXch + row * 8 + 4) = make_float4(g * fc_part[4], g * fc_part[5], g * fc_part[6], g * fc_part[7]);
-          asm volatile("bar.arrive 1, 256;" ::: "memory");
+        float part[kTcMaxClasses];
+#pragma unroll
+        for (int c = 0; c < kTcMaxClasses; ++c) part[c] = 0.0f;
+        if (emit) {                                                 // dynamic_rnn: zero output past the length
+#pragma unroll
+          for (int j = 0; j < kTcUnits; ++j) {
+            const float4 wa = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8 + 4);
+            part[0] = fmaf(h[j], wa.x, part[0]); part[1] = fmaf(h[j], wa.y, part[1]);
+            part[2] = fmaf(h[j], wa.z, part[2]); part[3] = fmaf(h[j], wa.w, part[3]);
+            part[4] = fmaf(h[j], wb.x, part[4]); part[5] = fmaf(h[j], wb.y, part[5]);
+            part[6] = fmaf(h[j], wb.z, part[6]); part[7] = fmaf(h[j], wb.w, part[7]);
+          }
+        }
+        if (ublk > 0) {
+          float* dst = sXch + ((ublk - 1) * kTcTile + row) * 8;
+          *reinterpret_cast<float4*>(dst) = make_float4(part[0], part[1], part[2], part[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(part[4], part[5], part[6], part[7]);
+          asm volatile("bar.arrive 1, 512;" ::: "memory");
         } else {
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, 512;" ::: "memory");
           if (ok) {
             float lg[8];
             float mx = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              lg[c] = (emit ? fc_part[c] : 0.0f) + sXch[row * 8 + c] + sFcb[c];
+              lg[c] = part[c] + sXch[row * 8 + c] + sXch[(kTcTile + row) * 8 + c] + sXch[(2 * kTcTile + row) * 8 + c] + sFcb[c];
               if (c < p.C) mx = fmaxf(mx, lg[c]);
             }
             float e[8], sum = 0.0f;
@@ -395,36 +387,29 @@ gru_tc_kernel(const GruTcParams p) {
       for (int t = 0; t < p.n; ++t, ++it) {
         const uint32_t par = it & 1;
         const bool more = t + 1 < p.n;
-        // ---- r gate: keep fp16(r*h) in registers until the u-gate MMAs have finished reading A_h.
-        // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c goes through the MUFU chain.
-        uint32_t rh[kTcUnits / 2];
         const bool tl = p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && t < 64;
+        // ---- r gate: keep fp16(r*h) in registers until the u-gate MMAs have finished reading A_h
+        uint32_t rh[kTcUnits / 2];
         if (tl) g_tc_timeline[t * 8 + 0] = clock64();
         mbar_acquire(&bars[kBarR], par);
         if (tl) g_tc_timeline[t * 8 + 1] = clock64();
-        {
-          uint32_t va[16], vb[16];
-          tc::ld16(tmem + lane_sel + colDr + u0, va);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[16];
+          tc::ld16(tmem + lane_sel + colDr + u0 + 16 * c, v);
           tc::wait_ld();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t (&cur)[16] = (c & 1) ? vb : va;
-            uint32_t (&nxt)[16] = (c & 1) ? va : vb;
-            if (c < 3) tc::ld16(tmem + lane_sel + colDr + u0 + 16 * (c + 1), nxt);
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              const int j = 16 * c + i;
-              const float r0 = sigmoid_pre(__uint_as_float(cur[i]), bR[j]);
-              const float r1 = sigmoid_pre(__uint_as_float(cur[i + 1]), bR[j + 1]);
-              rh[j / 2] = tc::pack_half2(r0 * h[j], r1 * h[j + 1]);
-            }
-            if (c < 3) tc::wait_ld();
+          for (int i = 0; i < 16; i += 2) {
+            const int j = 16 * c + i;
+            const float r0 = sigmoid_pre(__uint_as_float(v[i]), bR[j]);
+            const float r1 = sigmoid_pre(__uint_as_float(v[i + 1]), bR[j + 1]);
+            rh[j / 2] = tc::pack_half2(r0 * h[j], r1 * h[j + 1]);
           }
         }
         if (tl) g_tc_timeline[t * 8 + 2] = clock64();
         mbar_acquire(&bars[kBarU], par);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           const uint32_t v[8] = {rh[8 * c], rh[8 * c + 1], rh[8 * c + 2], rh[8 * c + 3],
                                  rh[8 * c + 4], rh[8 * c + 5], rh[8 * c + 6], rh[8 * c + 7]};
           tc::st8(my_ah + 8 * c, v);
@@ -433,22 +418,16 @@ gru_tc_kernel(const GruTcParams p) {
         if (tl) g_tc_timeline[t * 8 + 3] = clock64();
         if (more) load_x(t + 1);                                   // coalesced global loads in flight under the u gate
         // ---- u gate (beside the candidate MMAs): activated in place, D_u keeps u until the update reads it
-        {
-          uint32_t va[16], vb[16];
-          tc::ld16(tmem + lane_sel + colDu + u0, va);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[16];
+          tc::ld16(tmem + lane_sel + colDu + u0 + 16 * c, v);
           tc::wait_ld();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t (&cur)[16] = (c & 1) ? vb : va;
-            uint32_t (&nxt)[16] = (c & 1) ? va : vb;
-            if (c < 3) tc::ld16(tmem + lane_sel + colDu + u0 + 16 * (c + 1), nxt);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cur[i] = __float_as_uint(sigmoid_pre(__uint_as_float(cur[i]), bU[16 * c + i]));
-            tc::st16(tmem + lane_sel + colDu + u0 + 16 * c, cur);
-            if (c < 3) tc::wait_ld();
-          }
-          tc::wait_st();
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(sigmoid_pre(__uint_as_float(v[i]), bU[16 * c + i]));
+          tc::st16(tmem + lane_sel + colDu + u0 + 16 * c, v);
         }
+        tc::wait_st();
         // ---- candidate and state update: only what the next step's MMAs wait for
         if (tl) g_tc_timeline[t * 8 + 4] = clock64();
         mbar_acquire(&bars[kBarC], par);
@@ -458,62 +437,47 @@ gru_tc_kernel(const GruTcParams p) {
           tmem_publish(&bars[kBarAX]);
         }
         const bool live = t < len;
-        {
-          uint32_t ca[16], cb[16], ua[16], ub[16];
-          tc::ld16(tmem + lane_sel + colDc + u0, ca);
-          tc::ld16(tmem + lane_sel + colDu + u0, ua);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t vc[16], vu[16];
+          tc::ld16(tmem + lane_sel + colDc + u0 + 16 * c, vc);
+          tc::ld16(tmem + lane_sel + colDu + u0 + 16 * c, vu);
           tc::wait_ld();
+          uint32_t packed[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t (&vc)[16] = (c & 1) ? cb : ca;
-            uint32_t (&vu)[16] = (c & 1) ? ub : ua;
-            if (c < 3) {
-              tc::ld16(tmem + lane_sel + colDc + u0 + 16 * (c + 1), (c & 1) ? ca : cb);
-              tc::ld16(tmem + lane_sel + colDu + u0 + 16 * (c + 1), (c & 1) ? ua : ub);
+          for (int i = 0; i < 16; i += 2) {
+            const int j = 16 * c + i;
+            const float c0 = tanh_pre(__uint_as_float(vc[i]), bC[j]);
+            const float c1 = tanh_pre(__uint_as_float(vc[i + 1]), bC[j + 1]);
+            float n0 = fmaf(__uint_as_float(vu[i]), h[j] - c0, c0);          // u*h + (1-u)*c
+            float n1 = fmaf(__uint_as_float(vu[i + 1]), h[j + 1] - c1, c1);
+            if (!all_live) {                                       // dynamic_rnn: state carried past the length
+              n0 = live ? n0 : h[j];
+              n1 = live ? n1 : h[j + 1];
             }
-            uint32_t packed[8];
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              const int j = 16 * c + i;
-              const float c0 = tanh_pre(__uint_as_float(vc[i]), bC[j]);
-              const float c1 = tanh_pre(__uint_as_float(vc[i + 1]), bC[j + 1]);
-              float n0 = fmaf(__uint_as_float(vu[i]), h[j] - c0, c0);          // u*h + (1-u)*c
-              float n1 = fmaf(__uint_as_float(vu[i + 1]), h[j + 1] - c1, c1);
-              if (!all_live) {                                     // dynamic_rnn: state carried past the length
-                n0 = live ? n0 : h[j];
-                n1 = live ? n1 : h[j + 1];
-              }
-              h[j] = n0;
-              h[j + 1] = n1;
-              packed[i / 2] = tc::pack_half2(n0, n1);
-            }
-            if (more) tc::st8(my_ah + 8 * c, packed);
-            if (c < 3) tc::wait_ld();
+            h[j] = n0;
+            h[j + 1] = n1;
+            packed[i / 2] = tc::pack_half2(n0, n1);
           }
+          if (more) tc::st8(my_ah + 8 * c, packed);
         }
         if (more) tmem_publish(&bars[kBarAH]);                     // releases the next step's r/u MMAs
         if (tl) g_tc_timeline[t * 8 + 6] = clock64();
         // ---- outputs of this step, in the shadow of the next step's r-gate MMAs.  dynamic_rnn: zero output past the length
         const bool emit = all_live || live;
         if (!kLast) {
-          {   // tiled hand-off (rows past S are written too: the scratch is padded to whole tiles)
-            uint4* dst = reinterpret_cast<uint4*>(p.y_f16) + ((tile * p.n + t) * 16 + 8 * wg) * kTcTile + row;
+          // tiled hand-off (rows past S are written too: the scratch is padded to whole tiles)
+          uint4* dst = reinterpret_cast<uint4*>(p.y_f16) + ((tile * p.n + t) * 16 + 4 * ublk) * kTcTile + row;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              uint4 v;
-              v.x = emit ? tc::pack_half2(h[8 * q], h[8 * q + 1]) : 0u;
-              v.y = emit ? tc::pack_half2(h[8 * q + 2], h[8 * q + 3]) : 0u;
-              v.z = emit ? tc::pack_half2(h[8 * q + 4], h[8 * q + 5]) : 0u;
-              v.w = emit ? tc::pack_half2(h[8 * q + 6], h[8 * q + 7]) : 0u;
-              dst[q * kTcTile] = v;
-            }
+          for (int q = 0; q < 4; ++q) {
+            uint4 v;
+            v.x = emit ? tc::pack_half2(h[8 * q], h[8 * q + 1]) : 0u;
+            v.y = emit ? tc::pack_half2(h[8 * q + 2], h[8 * q + 3]) : 0u;
+            v.z = emit ? tc::pack_half2(h[8 * q + 4], h[8 * q + 5]) : 0u;
+            v.w = emit ? tc::pack_half2(h[8 * q + 6], h[8 * q + 7]) : 0u;
+            dst[q * kTcTile] = v;
           }
-        }
-        if (kLast) {                                               // in the shadow of the next step's r-gate MMAs
-#pragma unroll
-          for (int c = 0; c < kTcMaxClasses; ++c) fc_part[c] = 0.0f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) fc_accum(8 * c);
+        } else {
           fc_finish(t, emit);
         }
       }
@@ -527,11 +491,12 @@ gru_tc_kernel(const GruTcParams p) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tc::tmem_dealloc(tmem, 512);
 }
 
+
 static size_t gru_tc_smem_bytes(int ktot) {
-  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + kHidden * 8 + 8 + kTcTile * 8) + kNumBars * sizeof(uint64_t) + 16;
+  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + kHidden * 8 + 8 + 3 * kTcTile * 8) + kNumBars * sizeof(uint64_t) + 16;
 }
 
 // Pack one layer's TF kernels into the fp16 canonical [384, kxw+128] B operand: [Wx_hi | Wx_lo (split) | Wh].

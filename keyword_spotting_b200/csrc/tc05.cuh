@@ -150,6 +150,10 @@ __device__ __forceinline__ void st4(uint32_t taddr, const uint32_t (&v)[4]) {
                : "memory");
 }
 
+__device__ __forceinline__ void st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);      // .x (low 16 bits) = lo
   return *reinterpret_cast<const uint32_t*>(&h);

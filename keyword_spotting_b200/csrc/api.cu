@@ -177,6 +177,8 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
   }
   if (rc == KWS_OK) rc = upload(&m->fc_w, w->fc_w, static_cast<size_t>(H) * C);
   if (rc == KWS_OK) rc = upload(&m->fc_b, w->fc_b, C);
+  m->fc_w_host.assign(w->fc_w, w->fc_w + static_cast<size_t>(H) * C);
+  m->fc_b_host.assign(w->fc_b, w->fc_b + C);
   if (rc != KWS_OK) {
     free_model(m);
     return rc;

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/kws_b200.h"
 
@@ -84,6 +85,7 @@ struct kws_model {
   kws::LayerWeights layer[kws::kMaxLayers];
   float* fc_w = nullptr;          // [H, C]
   float* fc_b = nullptr;          // [C]
+  std::vector<float> fc_w_host, fc_b_host;   // host copies (the tensor-core kernel takes them as kernel parameters)
   // scratch owned by the model (grown by kws_model_reserve)
   int64_t cap_streams = 0;
   int32_t cap_frames = 0;

@@ -35,6 +35,7 @@
 // issued as three fp16 MMAs  x_hi*W_hi + x_lo*W_hi + x_hi*W_lo  (x = x_hi + x_lo, W = W_hi + W_lo; the
 // dropped lo*lo term is 2^-22 relative), i.e. at fp32-grade accuracy for +6 small MMAs per step.  With it the
 // deviation from the fp32 graph stays below 1e-3 (contract) on probabilities and state; see DESIGN.md.
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -72,6 +73,10 @@ struct GruTcParams {
   float* probs;                // [S, n, C]
   float* logits;               // [S, n, C] or null
   int timeline;                // record g_tc_timeline (debug)
+  // FC weights [128][8] + bias [8] by value: they sit in the constant bank, so the FC FMAs take them as
+  // (uniform) constant operands instead of 2 LDS.128 per hidden unit
+  float fcw[kHidden * kTcMaxClasses];
+  float fcb[kTcMaxClasses];
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -124,9 +129,7 @@ gru_tc_kernel(const GruTcParams p) {
   const int ktot = p.kxw + kHidden;                                                  // K extent of the packed weights
   unsigned char* sW = smem;                                                         // [384, ktot] fp16
   float* sBias = reinterpret_cast<float*>(smem + static_cast<size_t>(384) * ktot * 2);   // [384] pre-scaled
-  float* sFcw = sBias + 384;                                                        // [128][8]
-  float* sFcb = sFcw + kHidden * kTcMaxClasses;                                     // [8]
-  float* sXch = sFcb + kTcMaxClasses;                                               // [3][128][8] FC partials of unit blocks 1..3
+  float* sXch = sBias + 384;                                               // [3][128][8] FC partials of unit blocks 1..3
   uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 3 * kTcTile * kTcMaxClasses); // [kNumBars]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
@@ -149,13 +152,6 @@ gru_tc_kernel(const GruTcParams p) {
     for (int i = tid; i < n16; i += kTcThreads) reinterpret_cast<uint4*>(sW)[i] = __ldg(src + i);
     for (int i = tid; i < 384; i += kTcThreads)
       sBias[i] = p.bias[i] * (i < 2 * kHidden ? -kLog2e : 2.0f * kLog2e);
-    if (kLast) {
-      for (int i = tid; i < kHidden * kTcMaxClasses; i += kTcThreads) {
-        const int j = i / kTcMaxClasses, c = i % kTcMaxClasses;
-        sFcw[i] = c < p.C ? p.fc_w[j * p.C + c] : 0.0f;
-      }
-      if (tid < kTcMaxClasses) sFcb[tid] = tid < p.C ? p.fc_b[tid] : 0.0f;
-    }
   }
   tc::fence_proxy_async();            // weights written with generic stores, read by the MMA (async proxy)
   tc::fence_before_sync();
@@ -324,20 +320,30 @@ gru_tc_kernel(const GruTcParams p) {
       // FC + softmax of a step are computed right after its h' has been published, i.e. while the next step's
       // r-gate MMAs run: 32 units per thread, partial sums of unit blocks 1..3 handed to block 0 through smem.
       auto fc_finish = [&](int t_done, bool emit) {
+        const bool tl2 = p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && t_done < 32;
         float part[kTcMaxClasses];
 #pragma unroll
         for (int c = 0; c < kTcMaxClasses; ++c) part[c] = 0.0f;
         if (emit) {                                                 // dynamic_rnn: zero output past the length
 #pragma unroll
-          for (int j = 0; j < kTcUnits; ++j) {
-            const float4 wa = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(sFcw + (u0 + j) * 8 + 4);
-            part[0] = fmaf(h[j], wa.x, part[0]); part[1] = fmaf(h[j], wa.y, part[1]);
-            part[2] = fmaf(h[j], wa.z, part[2]); part[3] = fmaf(h[j], wa.w, part[3]);
-            part[4] = fmaf(h[j], wb.x, part[4]); part[5] = fmaf(h[j], wb.y, part[5]);
-            part[6] = fmaf(h[j], wb.z, part[6]); part[7] = fmaf(h[j], wb.w, part[7]);
+          // one copy per unit block so that every weight is a compile-time constant-bank address: the FMAs take
+          // c[0][imm] operands and the FC issues no load at all
+          auto fc_block = [&](auto UB) {
+            constexpr int kU0 = kTcUnits * decltype(UB)::value;
+#pragma unroll
+            for (int j = 0; j < kTcUnits; ++j) {
+#pragma unroll
+              for (int c = 0; c < kTcMaxClasses; ++c) part[c] = fmaf(h[j], p.fcw[(kU0 + j) * kTcMaxClasses + c], part[c]);
+            }
+          };
+          switch (ublk) {
+            case 0: fc_block(std::integral_constant<int, 0>{}); break;
+            case 1: fc_block(std::integral_constant<int, 1>{}); break;
+            case 2: fc_block(std::integral_constant<int, 2>{}); break;
+            default: fc_block(std::integral_constant<int, 3>{}); break;
           }
         }
+        if (tl2) g_tc_timeline[256 + t_done * 4 + 0] = clock64();
         if (ublk > 0) {
           float* dst = sXch + ((ublk - 1) * kTcTile + row) * 8;
           *reinterpret_cast<float4*>(dst) = make_float4(part[0], part[1], part[2], part[3]);
@@ -345,21 +351,22 @@ gru_tc_kernel(const GruTcParams p) {
           asm volatile("bar.arrive 1, 512;" ::: "memory");
         } else {
           asm volatile("bar.sync 1, 512;" ::: "memory");
+          if (tl2) g_tc_timeline[256 + t_done * 4 + 1] = clock64();
           if (ok) {
             float lg[8];
             float mx = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              lg[c] = part[c] + sXch[row * 8 + c] + sXch[(kTcTile + row) * 8 + c] + sXch[(2 * kTcTile + row) * 8 + c] + sFcb[c];
+              lg[c] = part[c] + sXch[row * 8 + c] + sXch[(kTcTile + row) * 8 + c] + sXch[(2 * kTcTile + row) * 8 + c] + p.fcb[c];
               if (c < p.C) mx = fmaxf(mx, lg[c]);
             }
             float e[8], sum = 0.0f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              e[c] = c < p.C ? expf(lg[c] - mx) : 0.0f;
+              e[c] = c < p.C ? ex2_approx((lg[c] - mx) * kLog2e) : 0.0f;    // 2 ulp: far inside the 1e-3 contract
               sum += e[c];
             }
-            const float inv = 1.0f / sum;
+            const float inv = rcp_approx(sum);                              // sum in [1, C]
             float* pr = p.probs + (s * p.n + t_done) * p.C;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
@@ -371,6 +378,7 @@ gru_tc_kernel(const GruTcParams p) {
                 if (c < p.C) lo[c] = lg[c];
             }
           }
+          if (tl2) g_tc_timeline[256 + t_done * 4 + 2] = clock64();
         }
       };
 
@@ -496,7 +504,7 @@ gru_tc_kernel(const GruTcParams p) {
 
 
 static size_t gru_tc_smem_bytes(int ktot) {
-  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + kHidden * 8 + 8 + 3 * kTcTile * 8) + kNumBars * sizeof(uint64_t) + 16;
+  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + 3 * kTcTile * 8) + kNumBars * sizeof(uint64_t) + 16;
 }
 
 // Pack one layer's TF kernels into the fp16 canonical [384, kxw+128] B operand: [Wx_hi | Wx_lo (split) | Wh].
@@ -568,6 +576,9 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     p.probs = a.probs;
     p.logits = a.logits;
     p.timeline = g_tc_timeline_on;
+    for (int j = 0; j < kHidden; ++j)
+      for (int c = 0; c < kTcMaxClasses; ++c) p.fcw[j * kTcMaxClasses + c] = c < m->cfg.num_classes ? m->fc_w_host[j * m->cfg.num_classes + c] : 0.0f;
+    for (int c = 0; c < kTcMaxClasses; ++c) p.fcb[c] = c < m->cfg.num_classes ? m->fc_b_host[c] : 0.0f;
     const size_t smem = gru_tc_smem_bytes(p.kxw + kHidden);
     const long blocks = ntiles < sm_count() ? ntiles : sm_count();
     const bool first = l == 0;

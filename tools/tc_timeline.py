@@ -24,4 +24,6 @@ for t in range(30):
     row = tl[t]
     nxt = tl[t + 1][0] if t + 1 < 30 else tl[0][7]
     d = [row[1] - row[0], row[2] - row[1], row[3] - row[2], row[4] - row[3], row[5] - row[4], row[6] - row[5], nxt - row[6]]
-    print(t, dict(zip(names, d)), "step", nxt - row[0])
+    print(t, dict(zip(names, [int(v) for v in d])), "step", int(nxt - row[0]))
+    f = buf[256 + 4 * t: 256 + 4 * t + 3]
+    print("     fc: partial %d  wait-others %d  softmax+store %d" % (f[0] - row[6], f[1] - f[0], f[2] - f[1]))

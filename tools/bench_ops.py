@@ -1,0 +1,54 @@
+"""Device timings of the custom ops (K4 decode, K5 octbit, K6 posenc) at BASELINE sizes -> one JSON object.
+
+    python tools/bench_ops.py            # needs a CUDA device
+"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from keyword_spotting_b200 import _lib
+from keyword_spotting_b200.octbit.octbit_ops import octbit_mat_mul
+from keyword_spotting_b200.octbit.octbit_graph import octize_weight_int8_signed
+from keyword_spotting_b200.positional_encoding.positional_encoding_op import positional_encoding
+from keyword_spotting_b200.utils import prediction
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(iters):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / iters
+
+
+out = {}
+rng = np.random.default_rng(0)
+g = torch.Generator(device="cuda").manual_seed(1)
+# ---- octbit: the three converted matmuls of the rnn_ctc graph at A = 131072 streams x 30 frames
+A = 131072 * 30
+for K, B in ((256, 256), (256, 128), (128, 6)):
+    x = torch.randn((A, K), device="cuda", generator=g)
+    # weights as the graph rewriter produces them: Xavier-normal fp32 -> octize_weight_int8_signed
+    wf = torch.randn((K, B), device="cuda", generator=g) * (2.0 / (K + B)) ** 0.5
+    w, scale, bias = octize_weight_int8_signed(wf)
+    ms = timeit(lambda: octbit_mat_mul(x, w, scale=scale, bias=bias), iters=5)
+    nbytes = A * K * 4 + B * K + A * B * 4
+    out["octbit_A%d_K%d_B%d" % (A, K, B)] = dict(ms=ms, algorithmic_GBps=nbytes / ms / 1e6, int8_TOPs=2.0 * A * B * K / ms / 1e9)
+    del x
+# ---- posenc: config 5 table and a large one
+for T, N in ((400, 128), (65536, 512)):
+    ms = timeit(lambda: positional_encoding(T, N), iters=20)
+    out["posenc_%dx%d" % (T, N)] = dict(ms=ms, GBps=T * N * 4 / ms / 1e6)
+# ---- decode: config 2, 4096 utterances x 298 frames, and the streaming window size
+lib = _lib.load()
+for S, T in ((4096, 298), (131072, 450)):
+    p = torch.rand((S, T, 6), device="cuda", generator=g)
+    p = p / p.sum(-1, keepdim=True)
+    for name, mode in (("ctc_decode", prediction.MODE_CTC_DECODE), ("ctc_decode2", prediction.MODE_CTC_DECODE2)):
+        ms = timeit(lambda: prediction.decode_batch(p, mode=mode, want_labels=False), iters=5)
+        out["%s_%dx%d" % (name, S, T)] = dict(ms=ms, GBps=S * T * 6 * 4 / ms / 1e6)
+print(json.dumps(out, indent=1))

@@ -148,6 +148,14 @@ int kws_ctc_decode(const float* probs, int64_t S, int32_t T, int32_t C, const in
                    const kws_decode_params* params, const char* keyword, int32_t* labels_out,
                    int32_t max_labels, int32_t* counts_out, int32_t* trigger_out, void* stream);
 
+/* Levenshtein distance of S (reference, hypothesis) label pairs: the integer that wer() divides by len(r)
+ * (utils/wer.py:4-41; used by the validation loop main.py:207-217 through WERCalculator, utils/wer.py:80-106).
+ *   ref [S, ld_ref] int32 with ref_len [S] valid entries per row, hyp likewise; dist_out [S] int32.
+ *   max_len: upper bound of all lengths, <= 254 (the reference's table is uint8, utils/wer.py:8).        */
+int kws_edit_distance(const int32_t* ref, const int32_t* ref_len, int64_t ld_ref, const int32_t* hyp,
+                      const int32_t* hyp_len, int64_t ld_hyp, int64_t S, int32_t max_len,
+                      int32_t* dist_out, void* stream);
+
 /* ----------------------------------------------------------------- server
  * The HotwordDetector.start loop (detector.py:148-209) for S lock-step streams
  * with all per-stream state resident in HBM: GRU state, carried PCM tail

@@ -70,6 +70,7 @@ _SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "kws_ctc_decode": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, POINTER(DecodeParams),
                                c_char_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "kws_edit_distance": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
     "kws_stream_create": (c_int, [c_void_p, POINTER(StreamConfig), POINTER(c_void_p)]),
     "kws_stream_destroy": (c_int, [c_void_p]),
     "kws_stream_reset": (c_int, [c_void_p, c_void_p]),

@@ -48,7 +48,60 @@ int decode_params_from_api(const kws_decode_params* in, int C, dec::Params* out)
   return KWS_OK;
 }
 
+// Levenshtein distance of S (reference, hypothesis) label pairs -- the integer the reference's WER divides by
+// len(r) (utils/wer.py:4-41).  One thread per pair, single rolling row; lengths <= 254 as in the reference
+// (its table is uint8).
+constexpr int kWerMaxLen = 254;
+__global__ void __launch_bounds__(128)
+edit_distance_kernel(const int* __restrict__ ref, const int* __restrict__ ref_len, long ld_ref,
+                     const int* __restrict__ hyp, const int* __restrict__ hyp_len, long ld_hyp, long S,
+                     int* __restrict__ dist) {
+  const long s = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (s >= S) return;
+  const int nr = ref_len[s], nh = hyp_len[s];
+  const int* r = ref + s * ld_ref;
+  const int* h = hyp + s * ld_hyp;
+  unsigned char row[kWerMaxLen + 1];              // d[i-1][*] rolling into d[i][*]
+  for (int j = 0; j <= nh; ++j) row[j] = static_cast<unsigned char>(j);
+  for (int i = 1; i <= nr; ++i) {
+    int diag = row[0];                            // d[i-1][j-1]
+    row[0] = static_cast<unsigned char>(i);
+    const int ri = r[i - 1];
+    for (int j = 1; j <= nh; ++j) {
+      const int up = row[j];                      // d[i-1][j]
+      int v;
+      if (ri == h[j - 1]) {
+        v = diag;
+      } else {
+        const int sub = diag + 1, ins = row[j - 1] + 1, del = up + 1;
+        v = sub < ins ? sub : ins;
+        v = v < del ? v : del;
+      }
+      diag = up;
+      row[j] = static_cast<unsigned char>(v);
+    }
+  }
+  dist[s] = row[nh];
+}
+
 }  // namespace kws
+
+extern "C" int kws_edit_distance(const int32_t* ref, const int32_t* ref_len, int64_t ld_ref, const int32_t* hyp,
+                                 const int32_t* hyp_len, int64_t ld_hyp, int64_t S, int32_t max_len,
+                                 int32_t* dist_out, void* stream) {
+  using namespace kws;
+  clear_error();
+  KWS_REQUIRE(S >= 0, "negative size");
+  if (S == 0) return KWS_OK;
+  KWS_REQUIRE(ref && ref_len && hyp && hyp_len && dist_out, "NULL pointer");
+  KWS_REQUIRE(max_len >= 0 && max_len <= kWerMaxLen, "sequences longer than %d labels are outside the reference's domain "
+              "(utils/wer.py:8, uint8 table)", kWerMaxLen);
+  KWS_REQUIRE(ld_ref >= max_len && ld_hyp >= max_len, "row stride smaller than max_len");
+  edit_distance_kernel<<<static_cast<unsigned>(ceil_div(S, 128)), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      ref, ref_len, ld_ref, hyp, hyp_len, ld_hyp, S, dist_out);
+  KWS_LAUNCH_OK("edit_distance_kernel");
+  return KWS_OK;
+}
 
 extern "C" int kws_ctc_decode(const float* probs, int64_t S, int32_t T, int32_t C, const int32_t* lens,
                               const kws_decode_params* params, const char* keyword, int32_t* labels_out,

@@ -58,6 +58,13 @@ class ModelWeights:
                    [f(a) for a in cand_kernel], [f(a) for a in cand_bias], f(fc_w), f(fc_b))
 
     @classmethod
+    def from_frozen_graph(cls, path_or_bytes, n_mel: Optional[int] = None):
+        """Weights of a frozen deployment ``graph.pb`` (main.py:339-348), read without TensorFlow
+        (keyword_spotting_b200/graph_pb.py)."""
+        from . import graph_pb
+        return graph_pb.rnn_ctc_weights(graph_pb.load_graph(path_or_bytes), n_mel=n_mel)
+
+    @classmethod
     def random_init(cls, config: Config, seed: int = 1234):
         """Random-init weights of the reference architecture: Xavier-normal GRU
         kernels (models/rnn_ctc.py:230-232), gate bias 1 / candidate bias 0 (TF

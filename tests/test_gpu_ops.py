@@ -255,3 +255,65 @@ def test_decode_full_size_properties():
         for s in range(0, S, 7):
             assert trig[s] == op.ctc_predict(labels[s], "1233")
         assert trig.sum() > 0
+
+
+def test_wer_matches_reference_golden():
+    """kws_edit_distance + the utils/wer.py mirrors vs the reference's own utils/wer.py outputs."""
+    from keyword_spotting_b200.utils import wer as kw
+    g = golden("wer_golden.npz")
+    refs = [g["ref"][g["ref_off"][i]:g["ref_off"][i + 1]].tolist() for i in range(len(g["ref_off"]) - 1)]
+    hyps = [g["hyp"][g["hyp_off"][i]:g["hyp_off"][i + 1]].tolist() for i in range(len(g["hyp_off"]) - 1)]
+    d = kw.edit_distance_batch(refs, hyps)
+    lens = np.asarray([len(r) for r in refs], np.float64)
+    got = np.where(lens > 0, d / np.maximum(lens, 1), d)
+    np.testing.assert_array_equal(got, g["wer"])
+    assert kw.wer(refs[5], hyps[5]) == g["wer"][5]
+    calc = kw.WERCalculator([0, 5])
+    np.testing.assert_array_equal(calc.cal_batch_wer(g["calc_r"], g["calc_h"]), g["calc_wer"])
+    bw = kw.batch_wer(int(g["sp_bs"]), g["sp_r_index"], g["sp_r_value"], g["sp_h_index"], g["sp_h_value"])
+    assert abs(bw - float(g["sp_wer"])) < 1e-12
+    with pytest.raises(ValueError):
+        kw.edit_distance_batch([[1] * 255], [[1]])
+
+
+def test_validation_harness_matches_reference_loop():
+    """evaluation.evaluate_softmax / validate vs the reference's validation arithmetic restated with the oracle
+    decoders (main.py:290-304): ctc_decode -> ctc_predict -> evaluate, summed over batches."""
+    import torch
+    from keyword_spotting_b200 import DeployModel, evaluation
+    from oracle import model as om, prediction as op
+    from tests._util import make_config, to_product_weights
+    g = golden("decode_golden.npz")
+    po = g["probs_off"]
+    T = 120
+    seqs = []
+    for i in range(len(po) - 1):
+        p = unpack(g["probs"], po, i, 6)
+        if len(p) >= T:
+            seqs.append(p[:T])
+    probs = np.stack(seqs[:64]).astype(np.float32)
+    rng = np.random.default_rng(3)
+    correct = rng.integers(0, 2, len(probs)).astype(np.int32)
+    want_res = [op.ctc_predict(op.ctc_decode(p), "1233") for p in probs]
+    want = op.evaluate(want_res, correct.tolist())
+    miss, target, fa, res = evaluation.evaluate_softmax(probs, correct)
+    assert (miss, target, fa) == tuple(want)
+    np.testing.assert_array_equal(res, want_res)
+    # whole loop on the model: mel batches with ragged lengths
+    ow = om.init_weights(seed=7, n_mel=40)
+    ow.fc_w = (ow.fc_w * 6).astype(np.float32)
+    dm = DeployModel(make_config(40), to_product_weights(ow), precision="fp32")
+    batches, tot = [], [0, 0, 0, 0]
+    for b in range(3):
+        mel = (np.abs(rng.standard_normal((16, 60, 40))) * 2).astype(np.float32)
+        lens = rng.integers(20, 61, 16).astype(np.int32)
+        corr = rng.integers(0, 2, 16).astype(np.int32)
+        batches.append((mel, lens, corr))
+        p, _, _ = om.mel_forward(mel, np.zeros((2, 16, 128), np.float32), ow, seq_len=lens)
+        r = [op.ctc_predict(op.ctc_decode(p[i, :lens[i]]), "1233") for i in range(16)]
+        m, t, f = op.evaluate(r, corr.tolist())
+        tot = [tot[0] + m, tot[1] + t, tot[2] + f, tot[3] + 16]
+    out = evaluation.validate(dm, batches)
+    assert [out["miss"], out["target"], out["false_accept"], out["total"]] == tot
+    assert "miss rate: %d/%d" % (tot[0], tot[1]) in out.report()
+    dm.close()

@@ -239,3 +239,19 @@ def test_stream_oracle_runs_and_resets():
         for s in np.nonzero(~r["speech"])[0]:
             assert len(so.queues[s].get_all()) == 1     # cleared, then this chunk pushed
     assert so.res.shape[1] == 320
+
+
+def _wer_golden():
+    g = golden("wer_golden.npz")
+    refs = [g["ref"][g["ref_off"][i]:g["ref_off"][i + 1]].tolist() for i in range(len(g["ref_off"]) - 1)]
+    hyps = [g["hyp"][g["hyp_off"][i]:g["hyp_off"][i + 1]].tolist() for i in range(len(g["hyp_off"]) - 1)]
+    return g, refs, hyps
+
+
+def test_wer_oracle_matches_reference_golden():
+    """oracle/wer.py against values produced by the reference's own utils/wer.py (tests/golden/make_wer_golden.py)."""
+    from oracle import wer as ow
+    g, refs, hyps = _wer_golden()
+    got = np.asarray([ow.wer(r, h) for r, h in zip(refs, hyps)])
+    np.testing.assert_array_equal(got, g["wer"])
+    assert max(len(r) for r in refs) == 254          # the reference's uint8 limit is covered

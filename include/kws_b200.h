@@ -235,6 +235,53 @@ int kws_octize_weight(const float* weight, int64_t in_dim, int64_t out_dim, int8
 int kws_positional_encoding(int32_t max_position, int32_t encoding_size, float* out,
                             void* stream);
 
+/* ----------------------------------------------------------------- attention_ctc
+ * The attention_ctc deployment forward pass (models/attention_ctc.py:73-128, :215-274; BASELINE config 5), the
+ * consumer of the positional_encoding op: combine_frame folding, input dense + positional encoding, num_layers x
+ * {8-head self-attention over all T' positions, add + layer_norm over (T', N), relu FFN, add + layer_norm},
+ * output dense (+relu) and softmax.  Utterances of one call have the same length (the graph has no padding mask). */
+typedef struct kws_attention kws_attention;
+
+typedef struct kws_attention_config {
+  int32_t n_mel;         /* 60  (config/attention_config.py:67)  */
+  int32_t combine_frame; /* 2   (:79)                             */
+  int32_t hidden;        /* 128 (:85) -- the only size the kernels are built for */
+  int32_t heads;         /* 8   (:84)                             */
+  int32_t num_layers;    /* 3   (:80)                             */
+  int32_t ffn;           /* 512 (:82)                             */
+  int32_t num_classes;   /* 6                                     */
+  int32_t use_relu;      /* 1   (:54) relu on the output layer    */
+} kws_attention_config;
+
+/* HOST pointers, fp32, dense-layer kernels as [in, out] (the [1,1,in,out] conv kernels of tf.layers.conv2d):
+ *   w_in [combine*n_mel, N], b_in [N]; per layer w_qkv [N, 3N], b_qkv [3N], ln1_g/ln1_b [N] (layer_norm after the
+ *   attention sub-layer), w_ff1 [N, F], b_ff1 [F], w_ff2 [F, N], b_ff2 [N], ln2_g/ln2_b [N]; w_out [N, C], b_out [C]. */
+typedef struct kws_attention_weights {
+  const float* w_in;
+  const float* b_in;
+  const float* w_qkv[8];
+  const float* b_qkv[8];
+  const float* ln1_g[8];
+  const float* ln1_b[8];
+  const float* w_ff1[8];
+  const float* b_ff1[8];
+  const float* w_ff2[8];
+  const float* b_ff2[8];
+  const float* ln2_g[8];
+  const float* ln2_b[8];
+  const float* w_out;
+  const float* b_out;
+} kws_attention_weights;
+
+int kws_attention_create(const kws_attention_config* cfg, const kws_attention_weights* host_weights, int device,
+                         kws_attention** out);
+int kws_attention_destroy(kws_attention* m);
+/* T' = T / combine_frame + 1 (models/attention_ctc.py:88-90). */
+int32_t kws_attention_frames(const kws_attention* m, int32_t T);
+/* mel [B, T, n_mel] (DEVICE, e.g. from kws_frontend_mel) -> probs_out [B, T', C]; logits_out may be NULL. */
+int kws_attention_forward(kws_attention* m, const float* mel, int64_t B, int32_t T, float* probs_out,
+                          float* logits_out, void* stream);
+
 /* ----------------------------------------------------------------- self-test
  * One 128 x N x K tensor-core product through the tcgen05 conventions the recurrent kernel builds on
  * (A in TMEM when ss_mode == 0, in shared memory when 1; B in shared memory; fp32 accumulate in TMEM).

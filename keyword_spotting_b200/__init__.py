@@ -12,6 +12,7 @@ Reference entry point                         -> here
   octbit/octbit_ops.py    octbit_mat_mul       octbit.octbit_ops.octbit_mat_mul
   octbit/octbit_graph.py  octize_weight_int8.. octbit.octbit_graph.octize_weight_int8_signed
   positional_encoding/positional_encoding_op.py positional_encoding.positional_encoding_op
+  models/attention_ctc.py DeployModel          attention_ctc.AttentionDeployModel
 """
 from . import _lib as _lib_mod
 
@@ -21,6 +22,8 @@ from ._lib import InvalidArgumentError, KwsCudaError  # noqa: E402
 from .config import Config, get_config  # noqa: E402
 from .rnn_ctc import DeployModel, ModelWeights  # noqa: E402
 from .streaming import StreamingDetector  # noqa: E402
+from .attention_ctc import AttentionConfig, AttentionDeployModel, AttentionWeights  # noqa: E402
 
 __all__ = ["Config", "get_config", "DeployModel", "ModelWeights", "StreamingDetector",
+           "AttentionConfig", "AttentionDeployModel", "AttentionWeights",
            "InvalidArgumentError", "KwsCudaError"]

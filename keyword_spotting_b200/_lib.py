@@ -53,6 +53,18 @@ class StreamConfig(Structure):
                 ("vad_threshold", c_int32), ("decode_thres", c_double), ("keyword", c_char * 20)]
 
 
+class AttentionConfig(Structure):
+    _fields_ = [(n, c_int32) for n in ("n_mel", "combine_frame", "hidden", "heads", "num_layers", "ffn",
+                                       "num_classes", "use_relu")]
+
+
+class AttentionWeights(Structure):
+    _fields_ = [("w_in", c_void_p), ("b_in", c_void_p)] + \
+               [(n, c_void_p * 8) for n in ("w_qkv", "b_qkv", "ln1_g", "ln1_b", "w_ff1", "b_ff1", "w_ff2", "b_ff2",
+                                            "ln2_g", "ln2_b")] + \
+               [("w_out", c_void_p), ("b_out", c_void_p)]
+
+
 _SIGNATURES = {
     "kws_last_error": (c_char_p, []),
     "kws_abi_version": (c_int, []),
@@ -87,6 +99,10 @@ _SIGNATURES = {
                                         c_void_p, c_void_p, c_size_t, c_void_p]),
     "kws_octize_weight": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
     "kws_positional_encoding": (c_int, [c_int32, c_int32, c_void_p, c_void_p]),
+    "kws_attention_create": (c_int, [POINTER(AttentionConfig), POINTER(AttentionWeights), c_int, POINTER(c_void_p)]),
+    "kws_attention_destroy": (c_int, [c_void_p]),
+    "kws_attention_frames": (c_int32, [c_void_p, c_int32]),
+    "kws_attention_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "kws_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kws_debug_tc_timeline": (c_int, [c_int, c_void_p, c_int]),
 }

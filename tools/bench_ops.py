@@ -51,4 +51,17 @@ for S, T in ((4096, 298), (131072, 450)):
     for name, mode in (("ctc_decode", prediction.MODE_CTC_DECODE), ("ctc_decode2", prediction.MODE_CTC_DECODE2)):
         ms = timeit(lambda: prediction.decode_batch(p, mode=mode, want_labels=False), iters=5)
         out["%s_%dx%d" % (name, S, T)] = dict(ms=ms, GBps=S * T * 6 * 4 / ms / 1e6)
+# ---- attention_ctc forward, config 5: batched 8 s utterances (T = 798 mel frames of 60 bands -> T' = 400)
+from keyword_spotting_b200 import AttentionConfig, AttentionDeployModel
+am = AttentionDeployModel(AttentionConfig())
+for B in (256, 1024):
+    mel = torch.rand((B, 798, 60), device="cuda", generator=g) * 2
+    ms = timeit(lambda: am.run_mel(mel), iters=3, warm=2)
+    flop = B * (400 * 120 * 128 * 2 + 3 * (400 * 128 * 384 * 2 + 2 * 8 * 400 * 400 * 16 * 2 + 2 * 400 * 128 * 512 * 2) + 400 * 128 * 6 * 2)
+    out["attention_mel_forward_B%d_8s" % B] = dict(ms=ms, utterances_per_s=B / ms * 1e3, audio_s_per_s=8.0 * B / ms * 1e3,
+                                                   TFLOPs=flop / ms / 1e9)
+pcm = (torch.randn((256, 128000), device="cuda", generator=g) * 0.05)
+ms = timeit(lambda: am(pcm), iters=3, warm=2)
+out["attention_pcm_forward_B256_8s"] = dict(ms=ms, audio_s_per_s=8.0 * 256 / ms * 1e3)
+am.close()
 print(json.dumps(out, indent=1))

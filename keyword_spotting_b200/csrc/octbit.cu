@@ -22,51 +22,9 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "octbit_common.cuh"
 
 namespace kws {
-
-struct OctbitHeader {        // first 256 bytes of the workspace
-  unsigned enc_min;          // order-preserving encodings of the running min / max
-  unsigned enc_max;
-  unsigned pad[62];
-};
-
-__device__ __forceinline__ unsigned enc_float(float f) {
-  unsigned u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float dec_float(unsigned e) {
-  unsigned u = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
-  return __uint_as_float(u);
-}
-
-struct QuantParams {
-  float bscale;
-  float offset;     // 127 (signed) or 0
-  int is_signed;
-};
-
-__device__ __forceinline__ QuantParams quant_params(const OctbitHeader* h) {
-  const float mn = dec_float(h->enc_min);
-  const float mx = dec_float(h->enc_max);
-  QuantParams p;
-  p.is_signed = mn < 0.0f;
-  if (p.is_signed) {
-    const float m = fmaxf(-mn, mx);
-    p.bscale = __fdiv_rn(m, 127.0f);
-    p.offset = 127.0f;
-  } else {
-    p.bscale = __fdiv_rn(mx, 254.0f);
-    p.offset = 0.0f;
-  }
-  return p;
-}
-
-__device__ __forceinline__ unsigned quant_one(float x, const QuantParams& p) {
-  if (p.bscale == 0.0f) return 0u;                       // 0/0: undefined in the reference
-  const float r = roundf(__fdiv_rn(x, p.bscale));        // C round(): half away from zero
-  return static_cast<unsigned>(static_cast<int>(r + p.offset)) & 0xffu;
-}
 
 __global__ void octbit_init_kernel(OctbitHeader* h) {
   h->enc_min = enc_float(FLT_MAX);      // std::numeric_limits<float>::max()    (:92)
@@ -128,19 +86,6 @@ octbit_quantize_kernel(const float* __restrict__ x, long n, const OctbitHeader* 
     q4[i] = quant_one(v.x, p) | (quant_one(v.y, p) << 8) | (quant_one(v.z, p) << 16) |
             (quant_one(v.w, p) << 24);
   }
-}
-
-__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
-
-__device__ __forceinline__ float octbit_epilogue(int l0, int l1, int l2, int l3, int is_signed,
-                                                 float bias, float scale) {
-  float o = 0.0f;                                   // output(batch,i) = 0          (:127-131)
-  o = __fadd_rn(o, static_cast<float>(l0));         // += val[m], m = 0..3          (:172-175)
-  o = __fadd_rn(o, static_cast<float>(l1));
-  o = __fadd_rn(o, static_cast<float>(l2));
-  o = __fadd_rn(o, static_cast<float>(l3));
-  if (is_signed) o = __fsub_rn(o, bias);            // -= biasvec(i)                (:176-178)
-  return __fmul_rn(o, scale);                       // *= scale                     (:179)
 }
 
 // ---------------------------------------------------------------- exact back end
@@ -357,10 +302,12 @@ extern "C" int kws_octbit_matmul(const float* x, const int8_t* w, const float* b
   if (blocks > sms * 8L) blocks = sms * 8L;
   octbit_minmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n, hdr);
   KWS_LAUNCH_OK("octbit_minmax_kernel");
-  octbit_quantize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n, hdr, reinterpret_cast<unsigned*>(q));
-  KWS_LAUNCH_OK("octbit_quantize_kernel");
-
   const bool fast = K <= 512 && B <= 4096;
+  const bool tc = octbit_tc_supported(A, B, K);       // tcgen05 kind::i8 with the quantiser fused in (octbit_tc.cu)
+  if (!tc) {
+    octbit_quantize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n, hdr, reinterpret_cast<unsigned*>(q));
+    KWS_LAUNCH_OK("octbit_quantize_kernel");
+  }
   if (fast) {
     KWS_CUDA_OK(cudaMemsetAsync(cand_count, 0, sizeof(int) * static_cast<size_t>(B), st));
     long cblocks = ceil_div(B * (K / 2), 256);
@@ -368,6 +315,7 @@ extern "C" int kws_octbit_matmul(const float* x, const int8_t* w, const float* b
     octbit_find_candidates_kernel<<<static_cast<unsigned>(cblocks), 256, 0, st>>>(
         w, static_cast<int>(B), static_cast<int>(K), cand_count, cand);
     KWS_LAUNCH_OK("octbit_find_candidates_kernel");
+    if (tc) return launch_octbit_tc(x, w, bias, scale, A, B, K, hdr, cand_count, cand, out, st);
     dim3 grid(static_cast<unsigned>(ceil_div(B, 64)), static_cast<unsigned>(ceil_div(A, 64)));
     KWS_REQUIRE(ceil_div(A, 64) <= 65535 * 32768LL, "A too large");
     if (grid.y > 65535) {

@@ -27,8 +27,9 @@
 //                                                    c = tanh(D_c), h' = c + u (h - c), FC partials, A_h <- h', arrive
 //     so the dependent chain of a step is  r-MMA(h) -> sigmoid -> cand-MMA(h) -> tanh,  with the u gate, all
 //     x-part MMAs, the softmax and the global loads/stores running beside it;
-//   * gate algebra in fp32 with ex2.approx / rcp.approx (2 MUFU per activation, 6 per hidden unit and step --
-//     the unit this kernel is bound by), biases pre-scaled by log2(e) so an activation is FFMA, EX2, FADD, RCP.
+//   * gate algebra in fp32 with ex2.approx / rcp.approx; activations are evaluated in pairs that share one
+//     reciprocal (3 MUFU per 2 activations, 4.5 per hidden unit and step -- the MUFU pipe is what this kernel is
+//     bound by), biases pre-scaled by log2(e).
 // Operands are fp16 (weights rounded once on the host, activations rounded when written to TMEM), accumulation
 // and all state fp32.  The layer-0 input projection is the exception: mel features are unbounded (tens for loud
 // audio) and a single fp16 rounding of x and W_x alone costs up to 3e-3 on the carried state, so that product is
@@ -98,6 +99,24 @@ __device__ __forceinline__ float sigmoid_pre(float a, float nb) {
 // tanh(a + b) with pb = 2*log2(e) * b:     1 - 2 / (1 + 2^(2*log2e*(a+b)))    FFMA, EX2, FADD, RCP, FFMA
 __device__ __forceinline__ float tanh_pre(float a, float pb) {
   return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(fmaf(a, 2.0f * kLog2e, pb))), 1.0f);
+}
+
+// Two activations for three MUFU operations: 1/d0 and 1/d1 from ONE reciprocal of d0*d1.  The exponents are
+// clamped to 63 so that the product stays finite (d <= 2^63 + 1; sigmoid below 1e-19 / tanh above 1 - 2e-19 are
+// returned exactly as the clamp leaves them -- far below fp32 resolution of the results).
+__device__ __forceinline__ void sigmoid2_pre(float a0, float nb0, float a1, float nb1, float& s0, float& s1) {
+  const float d0 = 1.0f + ex2_approx(fminf(fmaf(a0, -kLog2e, nb0), 63.0f));
+  const float d1 = 1.0f + ex2_approx(fminf(fmaf(a1, -kLog2e, nb1), 63.0f));
+  const float r = rcp_approx(d0 * d1);
+  s0 = r * d1;
+  s1 = r * d0;
+}
+__device__ __forceinline__ void tanh2_pre(float a0, float pb0, float a1, float pb1, float& c0, float& c1) {
+  const float d0 = 1.0f + ex2_approx(fminf(fmaf(a0, 2.0f * kLog2e, pb0), 63.0f));
+  const float d1 = 1.0f + ex2_approx(fminf(fmaf(a1, 2.0f * kLog2e, pb1), 63.0f));
+  const float r = rcp_approx(d0 * d1);
+  c0 = fmaf(-2.0f, r * d1, 1.0f);
+  c1 = fmaf(-2.0f, r * d0, 1.0f);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -325,7 +344,6 @@ gru_tc_kernel(const GruTcParams p) {
 #pragma unroll
         for (int c = 0; c < kTcMaxClasses; ++c) part[c] = 0.0f;
         if (emit) {                                                 // dynamic_rnn: zero output past the length
-#pragma unroll
           // one copy per unit block so that every weight is a compile-time constant-bank address: the FMAs take
           // c[0][imm] operands and the FC issues no load at all
           auto fc_block = [&](auto UB) {
@@ -409,8 +427,8 @@ gru_tc_kernel(const GruTcParams p) {
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             const int j = 16 * c + i;
-            const float r0 = sigmoid_pre(__uint_as_float(v[i]), bR[j]);
-            const float r1 = sigmoid_pre(__uint_as_float(v[i + 1]), bR[j + 1]);
+            float r0, r1;
+            sigmoid2_pre(__uint_as_float(v[i]), bR[j], __uint_as_float(v[i + 1]), bR[j + 1], r0, r1);
             rh[j / 2] = tc::pack_half2(r0 * h[j], r1 * h[j + 1]);
           }
         }
@@ -426,13 +444,19 @@ gru_tc_kernel(const GruTcParams p) {
         if (tl) g_tc_timeline[t * 8 + 3] = clock64();
         if (more) load_x(t + 1);                                   // coalesced global loads in flight under the u gate
         // ---- u gate (beside the candidate MMAs): activated in place, D_u keeps u until the update reads it
+        // (holding u in registers instead was measured slower: it pushes the gate threads past their 112 registers)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t v[16];
           tc::ld16(tmem + lane_sel + colDu + u0 + 16 * c, v);
           tc::wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(sigmoid_pre(__uint_as_float(v[i]), bU[16 * c + i]));
+          for (int i = 0; i < 16; i += 2) {
+            float u0v, u1v;
+            sigmoid2_pre(__uint_as_float(v[i]), bU[16 * c + i], __uint_as_float(v[i + 1]), bU[16 * c + i + 1], u0v, u1v);
+            v[i] = __float_as_uint(u0v);
+            v[i + 1] = __float_as_uint(u1v);
+          }
           tc::st16(tmem + lane_sel + colDu + u0 + 16 * c, v);
         }
         tc::wait_st();
@@ -455,8 +479,8 @@ gru_tc_kernel(const GruTcParams p) {
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             const int j = 16 * c + i;
-            const float c0 = tanh_pre(__uint_as_float(vc[i]), bC[j]);
-            const float c1 = tanh_pre(__uint_as_float(vc[i + 1]), bC[j + 1]);
+            float c0, c1;
+            tanh2_pre(__uint_as_float(vc[i]), bC[j], __uint_as_float(vc[i + 1]), bC[j + 1], c0, c1);
             float n0 = fmaf(__uint_as_float(vu[i]), h[j] - c0, c0);          // u*h + (1-u)*c
             float n1 = fmaf(__uint_as_float(vu[i + 1]), h[j + 1] - c1, c1);
             if (!all_live) {                                       // dynamic_rnn: state carried past the length

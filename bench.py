@@ -205,6 +205,19 @@ def load_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def load_traffic(S):
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
+    capture, scaled from the captured stream count to S; None when the capture file is absent."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    d = json.load(open(path))
+    k = S / float(d["streams"])
+    out = {name: (v["dram_bytes_read"] + v["dram_bytes_write"]) * k for name, v in d["kernels"].items()}
+    out["_source"] = d["source"]
+    return out
+
+
 def make_chunks(torch, S, n_buf, device, seed):
     """n_buf distinct [S, 4800] int16 chunks on the device: per-stream noise level log-uniform in [30, 3000] LSB,
     ~30% of (stream, chunk) cells near-silent so the VAD reset fires."""
@@ -304,15 +317,20 @@ def run_ours(args, rank, world, local_rank):
     flop_per_launch = S * FRAMES * GRU_FLOP_PER_FRAME / cfg.num_layers
     achieved_tf = flop_per_launch / (gru_launch_ms * 1e-3) / 1e12
     kname = "gru_tc_kernel" if args.precision == "tc" else "gru_layer_kernel"
+    traffic = load_traffic(S) if args.precision == "tc" else {}
+    gru_traffic = None
+    if "gru_tc_kernel<0,1>" in traffic:
+        gru_traffic = 0.5 * (traffic["gru_tc_kernel<0,1>"] + traffic["gru_tc_kernel<1,0>"])   # mean of the two launches
     roof_gru = dict(kernel=kname, bound="tensor", achieved=achieved_tf, peak=peaks["bf16_sustained"],
-                    unit="TFLOP/s", frac=achieved_tf / peaks["bf16_sustained"], traffic=None, launch_ms=gru_launch_ms,
+                    unit="TFLOP/s", frac=achieved_tf / peaks["bf16_sustained"], traffic=gru_traffic, launch_ms=gru_launch_ms,
                     peak_source=peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                     note=("tcgen05 kind::f16 (fp16 operands, fp32 accumulate); " if args.precision == "tc" else
                           "exact fp32 FFMA kernel measured against the tensor-pipe peak; ") +
                          "algorithmic FLOP = 327,168 per frame (GRU 325,632 + FC 1,536), one launch per layer")
     fe_gbs = S * FE_BYTES_PER_STREAM_CHUNK / (fe_launch_ms * 1e-3) / 1e9
     roof_fe = dict(kernel="frontend_kernel", bound="hbm", achieved=fe_gbs, peak=peaks["hbm"], unit="GB/s",
-                   frac=fe_gbs / peaks["hbm"], traffic=None, launch_ms=fe_launch_ms,
+                   frac=fe_gbs / peaks["hbm"], traffic=traffic.get("frontend_kernel"), launch_ms=fe_launch_ms,
+                   algorithmic_bytes=S * FE_BYTES_PER_STREAM_CHUNK, traffic_source=traffic.get("_source"),
                    peak_source=peaks["source"] + ", copy bandwidth",
                    note="algorithmic bytes = %d per stream-chunk (int16 PCM in, carried tail r+w, fp32 mel out, flags); "
                         "one launch per step; timed here on a 5120-sample input without the fused VAD/tail work" % FE_BYTES_PER_STREAM_CHUNK)

@@ -72,14 +72,14 @@ class WERCalculator(object):
         self._ignore_label_set = set(ignore_label_list)
 
     def remove_residual(self, inputs):
-        outputs = []
-        for i in inputs:
-            if i == -1:
-                return np.asarray(outputs)
-            if i in self._ignore_label_set:
-                continue
-            outputs.append(i)
-        return np.asarray(outputs)
+        """Labels up to (not including) the first -1 terminator, without the ignored ones (utils/wer.py:84-92)."""
+        seq = np.asarray(inputs).ravel()
+        stop = np.flatnonzero(seq == -1)
+        if stop.size:
+            seq = seq[:stop[0]]
+        if self._ignore_label_set:
+            seq = seq[~np.isin(seq, list(self._ignore_label_set))]
+        return seq
 
     def cal_batch_wer(self, batch_r, batch_h):
         refs = [self.remove_residual(r) for r in batch_r]
@@ -89,12 +89,12 @@ class WERCalculator(object):
         return np.where(lens > 0, d / np.maximum(lens, 1.0), 0.0)          # empty reference -> 0. (:97-99)
 
     def cal_topk_wers(self, batch_r, batch_h, batch_size, nums_gpu, topk, max_topk):
-        list_wers = []
-        for gpu_index in np.arange(nums_gpu):
-            wers = []
-            r = batch_r[gpu_index * batch_size: (gpu_index + 1) * batch_size]
-            h = batch_h[gpu_index * batch_size * max_topk: (gpu_index + 1) * batch_size * max_topk]
-            for i in np.arange(topk):
-                wers.append(self.cal_batch_wer(r, h[i * batch_size: (i + 1) * batch_size]))
-            list_wers.extend(np.min(np.vstack(wers), axis=0))
-        return list_wers
+        """Best-of-topk WER per utterance for hypotheses laid out [gpu][k][utterance] (utils/wer.py:108-124)."""
+        best = []
+        for g in range(int(nums_gpu)):
+            refs = batch_r[g * batch_size:(g + 1) * batch_size]
+            hyp0 = g * batch_size * max_topk
+            per_k = [self.cal_batch_wer(refs, batch_h[hyp0 + k * batch_size: hyp0 + (k + 1) * batch_size])
+                     for k in range(int(topk))]
+            best.extend(np.min(np.vstack(per_k), axis=0))
+        return best

@@ -344,3 +344,45 @@ def test_streaming_server_tensor_core_mode():
     assert n_lab > 50, n_lab
     det.close()
     dm.close()
+
+
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_stream_objects_on_concurrent_cuda_streams_match_one_big_object(precision):
+    """bench.py's latency mode: the streams of a GPU served as several stream objects on their own CUDA streams.
+    Every per-step buffer (mel, hand-off, probs, state, window) is private to the object, so the waves may overlap
+    freely and must reproduce exactly what one object holding all the streams computes."""
+    import torch
+    from keyword_spotting_b200 import DeployModel, StreamingDetector
+    from oracle import model as om
+    ow = _boost_fc(om.init_weights(seed=21, n_mel=40))
+    dm = DeployModel(make_config(40), to_product_weights(ow), precision=precision)
+    W, Sw, chunks, chunk = 4, 160, 6, 4800
+    S = W * Sw
+    rng = np.random.default_rng(77)
+    pcm = torch.from_numpy(synth_pcm16(rng, S, chunk * chunks, silent_frac=0.2)).cuda()
+    big = StreamingDetector(dm, S, keyword="1")
+    waves = [StreamingDetector(dm, Sw, keyword="1") for _ in range(W)]
+    streams = [torch.cuda.Stream() for _ in range(W)]
+    torch.cuda.synchronize()
+    for c in range(chunks):
+        blk = pcm[:, c * chunk:(c + 1) * chunk].contiguous()
+        trig, probs, nfr = big.step(blk, want_probs=True)
+        outs = []
+        for w in range(W):
+            streams[w].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[w]):
+                outs.append(waves[w].step(blk[w * Sw:(w + 1) * Sw], want_probs=True))
+        for s in streams:
+            torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for w in range(W):
+            sl = slice(w * Sw, (w + 1) * Sw)
+            assert torch.equal(outs[w][0], trig[sl]), (c, w)
+            assert torch.equal(outs[w][2], nfr[sl])
+            assert torch.equal(outs[w][1], probs[sl]), (c, w)       # same kernels, same tiles of 128? not necessarily:
+    st_big = big.state()
+    for w in range(W):
+        assert torch.equal(waves[w].state(), st_big[:, w * Sw:(w + 1) * Sw])
+    for d in waves + [big]:
+        d.close()
+    dm.close()

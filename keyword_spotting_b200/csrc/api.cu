@@ -60,10 +60,8 @@ void pack_tc_weights(const float* gates_kernel, const float* cand_kernel, int in
 static void free_model(kws_model* m) {
   if (!m) return;
   cudaFree(m->mel_basis);
-  cudaFree(m->mel.start);
-  cudaFree(m->mel.count);
-  cudaFree(m->mel.offset);
-  cudaFree(m->mel.weight);
+  cudaFree(m->mel.quad_w);
+  cudaFree(m->mel.quad_m);
   cudaFree(m->twiddle400);
   for (int l = 0; l < kMaxLayers; ++l) {
     cudaFree(m->layer[l].gates_kernel);
@@ -123,31 +121,14 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
   m->device = device;
   const int M = cfg->n_mel, H = kHidden, C = cfg->num_classes;
   int rc = upload(&m->mel_basis, w->mel_basis, static_cast<size_t>(kBins) * M);
-  // per-band non-zero ranges of the basis (exact for any basis: zeros contribute nothing)
-  std::vector<int> start(M, 0), count(M, 0), offset(M, 0);
-  std::vector<float> packed;
-  for (int b = 0; b < M && rc == KWS_OK; ++b) {
-    int lo = -1, hi = -1;
-    for (int k = 0; k < kBins; ++k)
-      if (w->mel_basis[static_cast<size_t>(k) * M + b] != 0.0f) {
-        if (lo < 0) lo = k;
-        hi = k;
-      }
-    offset[b] = static_cast<int>(packed.size());                      // always a multiple of 4 (float4 reads)
-    if (lo >= 0) {
-      start[b] = lo;
-      count[b] = (hi - lo + 1 + 3) / 4 * 4;                           // padded with zero weights
-      for (int k = lo; k < lo + count[b]; ++k)
-        packed.push_back(k <= hi ? w->mel_basis[static_cast<size_t>(k) * M + b] : 0.0f);
-    }
-    if (count[b] > m->mel.max_count) m->mel.max_count = count[b];
+  {
+    // non-zero part of the basis as balanced per-warp quad lists (exact for any basis: zeros contribute nothing)
+    std::vector<float4> qw;
+    std::vector<int2> qm;
+    kws::build_mel_quads(w->mel_basis, M, &qw, &qm, &m->mel.quads_per_warp);
+    if (rc == KWS_OK) rc = upload(&m->mel.quad_w, qw.data(), qw.size());
+    if (rc == KWS_OK) rc = upload(&m->mel.quad_m, qm.data(), qm.size());
   }
-  m->mel.nnz = static_cast<int>(packed.size());
-  if (packed.empty()) packed.push_back(0.0f);
-  if (rc == KWS_OK) rc = upload(&m->mel.start, start.data(), start.size());
-  if (rc == KWS_OK) rc = upload(&m->mel.count, count.data(), count.size());
-  if (rc == KWS_OK) rc = upload(&m->mel.offset, offset.data(), offset.size());
-  if (rc == KWS_OK) rc = upload(&m->mel.weight, packed.data(), packed.size());
   std::vector<float2> tw(20 * 52);          // periodic k2-major table of W400^(n1*k2) (fft400.cuh: kTwStride = 52)
   for (int k2 = 0; k2 < 20; ++k2)
     for (int j = 0; j < 52; ++j) {

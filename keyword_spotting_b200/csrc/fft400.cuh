@@ -42,8 +42,32 @@ constexpr int kBufSlots = kR * kRowStride;   // 420 complex slots
 constexpr int kPairWindow = 560;  // samples spanned by two consecutive frames (160 + 400)
 constexpr int kBins = kN / 2 + 1; // 201
 
+// Complex add / subtract / real scaling / rotation by +-i are pairwise operations, so on the device each is ONE
+// packed f32x2 instruction (FADD2 / FFMA2 / FMUL2 of sm_100a; the half swap of the +-i rotations is a free
+// register-half selector of the packed operand) instead of two scalar ones -- K1 is bound by instruction issue.
+#if defined(__CUDA_ARCH__)
+KWS_HD float2 as_f2(cpx a) { return make_float2(a.re, a.im); }
+KWS_HD cpx as_cpx(float2 a) { return cpx{a.x, a.y}; }
+KWS_HD cpx cadd(cpx a, cpx b) { return as_cpx(__fadd2_rn(as_f2(a), as_f2(b))); }
+KWS_HD cpx csub(cpx a, cpx b) { return as_cpx(__ffma2_rn(as_f2(b), make_float2(-1.0f, -1.0f), as_f2(a))); }
+KWS_HD cpx caxpy(float s, cpx b, cpx a) { return as_cpx(__ffma2_rn(as_f2(b), make_float2(s, s), as_f2(a))); }   // a + s*b
+KWS_HD cpx cscale(float s, cpx b) { return as_cpx(__fmul2_rn(as_f2(b), make_float2(s, s))); }                     // s*b
+KWS_HD cpx csub_i(cpx a, cpx b) { return as_cpx(__ffma2_rn(make_float2(b.im, b.re), make_float2(1.0f, -1.0f), as_f2(a))); }  // a - i*b
+KWS_HD cpx cadd_i(cpx a, cpx b) { return as_cpx(__ffma2_rn(make_float2(b.im, b.re), make_float2(-1.0f, 1.0f), as_f2(a))); }  // a + i*b
+// (a.re^2 + b.im^2, a.im^2 + b.re^2)
+KWS_HD cpx cross_sq(cpx a, cpx b) {
+  const float2 bs = make_float2(b.im, b.re);
+  return as_cpx(__ffma2_rn(bs, bs, __fmul2_rn(as_f2(a), as_f2(a))));
+}
+#else
 KWS_HD cpx cadd(cpx a, cpx b) { return cpx{a.re + b.re, a.im + b.im}; }
 KWS_HD cpx csub(cpx a, cpx b) { return cpx{a.re - b.re, a.im - b.im}; }
+KWS_HD cpx caxpy(float s, cpx b, cpx a) { return cpx{a.re + s * b.re, a.im + s * b.im}; }
+KWS_HD cpx cscale(float s, cpx b) { return cpx{s * b.re, s * b.im}; }
+KWS_HD cpx csub_i(cpx a, cpx b) { return cpx{a.re + b.im, a.im - b.re}; }
+KWS_HD cpx cadd_i(cpx a, cpx b) { return cpx{a.re - b.im, a.im + b.re}; }
+KWS_HD cpx cross_sq(cpx a, cpx b) { return cpx{a.re * a.re + b.im * b.im, a.im * a.im + b.re * b.re}; }
+#endif
 KWS_HD cpx cmul(cpx a, cpx b) { return cpx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 
 // forward DFT-4, in place (W4 = -i)
@@ -51,8 +75,8 @@ KWS_HD void dft4(cpx& a0, cpx& a1, cpx& a2, cpx& a3) {
   const cpx t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
   a0 = cadd(t0, t2);
   a2 = csub(t0, t2);
-  a1 = cpx{t1.re + t3.im, t1.im - t3.re};   // t1 - i*t3
-  a3 = cpx{t1.re - t3.im, t1.im + t3.re};   // t1 + i*t3
+  a1 = csub_i(t1, t3);
+  a3 = cadd_i(t1, t3);
 }
 
 // forward DFT-5, in place (W5 = exp(-2*pi*i/5))
@@ -62,15 +86,15 @@ KWS_HD void dft5(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4) {
   const float s1 = 0.95105651629515357f;    // sin(2pi/5)
   const float s2 = 0.58778525229247313f;    // sin(4pi/5)
   const cpx t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
-  const cpx m1 = cpx{a0.re + c1 * t1.re + c2 * t2.re, a0.im + c1 * t1.im + c2 * t2.im};
-  const cpx m2 = cpx{a0.re + c2 * t1.re + c1 * t2.re, a0.im + c2 * t1.im + c1 * t2.im};
-  const cpx n1 = cpx{s1 * t3.re + s2 * t4.re, s1 * t3.im + s2 * t4.im};
-  const cpx n2 = cpx{s2 * t3.re - s1 * t4.re, s2 * t3.im - s1 * t4.im};
-  a0 = cpx{a0.re + t1.re + t2.re, a0.im + t1.im + t2.im};
-  a1 = cpx{m1.re + n1.im, m1.im - n1.re};   // m1 - i*n1
-  a4 = cpx{m1.re - n1.im, m1.im + n1.re};   // m1 + i*n1
-  a2 = cpx{m2.re + n2.im, m2.im - n2.re};   // m2 - i*n2
-  a3 = cpx{m2.re - n2.im, m2.im + n2.re};   // m2 + i*n2
+  const cpx m1 = caxpy(c2, t2, caxpy(c1, t1, a0));
+  const cpx m2 = caxpy(c1, t2, caxpy(c2, t1, a0));
+  const cpx n1 = caxpy(s2, t4, cscale(s1, t3));
+  const cpx n2 = caxpy(-s1, t4, cscale(s2, t3));
+  a0 = cadd(cadd(a0, t1), t2);
+  a1 = csub_i(m1, n1);
+  a4 = cadd_i(m1, n1);
+  a2 = csub_i(m2, n2);
+  a3 = cadd_i(m2, n2);
 }
 
 // where output k of the prime-factor DFT-20 sits in the in-place array
@@ -117,43 +141,43 @@ KWS_HD void stage2_col(int k2, cpx* buf, cpx (&v)[20]) {
   for (int k1 = kR / 2; k1 < kR; ++k1) buf[k1 * kRowStride + k2] = v[pfa_slot(k1)];
 }
 
-KWS_HD float mag_of(float re, float im, float scale) {
+KWS_HD float sqrt_fast(float x) {
 #if defined(__CUDA_ARCH__)
   float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(re * re + im * im));
-  return scale * r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
-  return scale * __builtin_sqrtf(re * re + im * im);
+  return __builtin_sqrtf(x);
 #endif
 }
 
-// |A[k]|, |B[k]| for the bins k = 20*k1 + k2 <= 200 of column k2 (after a barrier).  `v` is the register
+// 2|A[k]|, 2|B[k]| for the bins k = 20*k1 + k2 <= 200 of column k2 (after a barrier).  `v` is the register
 // state left by stage2_col; Z[400-k] comes from the mirror column's published rows 10..19.  Results go to
-// mag_a[k*mag_stride] and mag_b[k*mag_stride] (any memory that nobody is reading during this phase).
-// `scale` = 1/2 times the sample scale (the DFT is linear, so int16 samples are transformed unscaled and 2^-15
-// is applied here).
-KWS_HD void untangle_col(int k2, const cpx (&v)[20], const cpx* buf, float scale, float* mag_a, float* mag_b,
-                         int mag_stride) {
+// mag_a[k1*k1_stride] and mag_b[k1*k1_stride]: the caller passes the address of bin k2 and the distance between
+// bins 20 apart (any memory that nobody is reading during this phase).
+// The factor 1/2 (and the sample scale: the DFT is linear, so int16 samples are transformed unscaled) is left
+// to the consumer -- the mel projection applies it once per band instead of once per bin.
+KWS_HD void untangle_col(int k2, const cpx (&v)[20], const cpx* buf, float* mag_a, float* mag_b, int k1_stride) {
   const int mcol = k2 == 0 ? 0 : kR - k2;          // column of Z[400 - k]
   const int mrow0 = k2 == 0 ? kR : kR - 1;         // its row is mrow0 - k1
 #pragma unroll
   for (int k1 = 0; k1 < kR / 2; ++k1) {
-    const int k = kR * k1 + k2;
     const cpx zk = v[pfa_slot(k1)];
     int mrow = mrow0 - k1;
     const bool self = mrow == kR;                   // k == 0: Z[400] = Z[0] = zk
     if (self) mrow = kR - 1;                        // any published slot; the value is discarded
     cpx zm = buf[mrow * kRowStride + mcol];
     if (self) zm = zk;
-    const float ar = zk.re + zm.re, ai = zk.im - zm.im;   // 2*A[k]
-    const float br = zk.re - zm.re, bi = zk.im + zm.im;   // 2i*B[k] rotated: same modulus
-    mag_a[k * mag_stride] = mag_of(ar, ai, scale);
-    mag_b[k * mag_stride] = mag_of(br, bi, scale);
+    // 2*A[k] = (sp.re, sm.im);  2i*B[k] (same modulus as 2*B[k]) = (sm.re, sp.im)
+    const cpx sp = cadd(zk, zm), sm = csub(zk, zm);
+    const cpx sq = cross_sq(sp, sm);                // (|2A|^2, |2B|^2)
+    mag_a[k1 * k1_stride] = sqrt_fast(sq.re);
+    mag_b[k1 * k1_stride] = sqrt_fast(sq.im);
   }
   if (k2 == 0) {                                    // k = 200 = 400 - 200: its own mirror
     const cpx z = v[pfa_slot(kR / 2)];
-    mag_a[(kN / 2) * mag_stride] = mag_of(2.0f * z.re, 0.0f, scale);
-    mag_b[(kN / 2) * mag_stride] = mag_of(0.0f, 2.0f * z.im, scale);
+    mag_a[(kR / 2) * k1_stride] = 2.0f * (z.re < 0.0f ? -z.re : z.re);
+    mag_b[(kR / 2) * k1_stride] = 2.0f * (z.im < 0.0f ? -z.im : z.im);
   }
 }
 

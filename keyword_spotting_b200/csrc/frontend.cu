@@ -13,12 +13,19 @@
 // thread t = 20*pair + column owns one DFT-20 column of its pair in both stages of the packed-real 20x20 FFT
 // (fft400.cuh).  The item's PCM (5360 samples) is staged once in shared memory as fp32 with coalesced 16-byte
 // loads; every 320-sample block is skewed by 20 floats so that the 32 lanes of a warp -- which straddle two
-// pairs -- read 32 distinct banks.  int16 samples are transformed unscaled (the DFT is linear) and 2^-15 is
-// folded into the magnitude.  Magnitudes go to shared memory transposed ([bin][frame]) so that the mel
-// projection runs with lane = frame and warp-uniform bands: it uses the per-band non-zero bin ranges of the basis
-// found at model creation (~2*201 FMAs per frame for a triangular filterbank, exact for any dense basis) with
-// broadcast weight reads and conflict-free magnitude reads; the [32, M] result tile leaves as one contiguous
-// block.  Persistent grid: (resident CTAs per SM) x 148 SMs, grid-stride over work items.
+// pairs -- read 32 distinct banks.  int16 PCM is fetched four samples per load (8 bytes) and the NEXT work item's
+// loads are issued before the mel projection of the current one, so their latency is hidden behind it.  int16
+// samples are transformed unscaled (the DFT is linear); 2^-15 and the 1/2 of the two-for-one untangling are applied
+// once per mel band.  Magnitudes go to shared memory transposed ([bin][frame]) so that the mel projection runs
+// with lane = frame and warp-uniform weights: the non-zero part of the basis is cut at model creation into "quads"
+// (4 consecutive bins of one band, build_mel_quads), whole bands are dealt to the 10 warps so that every warp gets
+// the same number of quads (longest-band-first), and the kernel runs one flat, branch-free loop over its quads
+// (~2*201 FMAs per frame for a triangular filterbank, exact for any dense basis) with broadcast weight reads and
+// conflict-free magnitude reads; the [32, M] result tile leaves as one contiguous block.  Persistent grid:
+// (resident CTAs per SM) x 148 SMs, grid-stride over work items.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "fft400.cuh"
 
@@ -34,14 +41,20 @@ constexpr int kFeBlock = 2 * kHop;                   // 320 samples between cons
 constexpr int kFeSkew = 20;                          // floats of skew per 320-sample block
 constexpr int kFeWinSamples = kFePairs * kFeBlock + (kFft - kHop);       // 5360
 constexpr int kFeWinRounds = (kFeWinSamples + kFeThreads - 1) / kFeThreads;   // 17
+constexpr int kFeQuadRounds = (kFeWinSamples + 4 * kFeThreads - 1) / (4 * kFeThreads);      // 5 (int16: 4 samples per load)
+constexpr int kFeLastQuads = (kFeWinSamples - 4 * kFeThreads * (kFeQuadRounds - 1)) / 4;    // 60 threads in the last round
+static_assert(kFeWinSamples % 4 == 0 && kFeBlock % 4 == 0, "quads must not straddle a skew boundary");
+constexpr int kFeQuadSmemMax = 1536;                 // quads kept in shared memory (24 B each); more -> read from global
 constexpr int kFeItemHop = kFePairs * kFeBlock;      // 5120 samples between consecutive items of a stream
-constexpr int kFeMagStride = 33;                     // floats per bin row of the transposed magnitudes [201][33]
+constexpr int kFeMagStride = 66;                     // floats per row of the transposed magnitudes [102 bin pairs][32 slots][2] (+2 pad)
 // the window (5360 samples + skew) and the transposed magnitudes share one region: the window is dead after stage 1
 constexpr int kFeWinFloats = kFeWinRounds * (kFeBlock + kFeSkew);        // 5780 (position tid + 340*round)
-constexpr int kFeMagRows = fft::kBins + 3;           // band ranges are padded to multiples of 4 bins: rows 201..203 stay zero
-constexpr int kFeRegionFloats = kFeMagRows * kFeMagStride > kFeWinFloats ? kFeMagRows * kFeMagStride : kFeWinFloats;
-static_assert(kFeWinFloats <= fft::kBins * kFeMagStride, "the window must not reach the zero rows");
-static_assert((kFeRegionFloats * 4) % 16 == 0, "mel weights follow the region and are read as float4");
+constexpr int kFeMagRows = (fft::kBins + 3) / 2;     // quads are 4 bins from an even bin: bins 201..203 stay zero
+constexpr int kFeMagFloats = kFeMagRows * kFeMagStride;
+constexpr int kFeMagLive = (fft::kBins / 2) * kFeMagStride;   // rows below hold only written bins (0..199)
+constexpr int kFeRegionFloats = kFeMagFloats > kFeWinFloats ? kFeMagFloats : kFeWinFloats;
+static_assert(kFeWinFloats <= kFeMagLive, "the window must not reach the rows that hold the zero bins");
+static_assert((kFeRegionFloats * 4) % 16 == 0, "mel quads follow the region and are read as float4");
 
 struct FrontendParams {
   PcmSource src;
@@ -51,14 +64,13 @@ struct FrontendParams {
   const int* nframes;       // [S] or null -> frames from the signal length
   int n_mel;
   const cpx* twiddle;       // [20*52] periodic k2-major table (fft::kTwSlots)
-  const int* mel_start;
-  const int* mel_count;
-  const int* mel_offset;
-  const float* mel_weight;
-  int mel_nnz;
+  const float4* mel_qw;     // [10 warps][quads_per_warp] weights of 4 consecutive bins
+  const int2* mel_qm;       // same shape: byte offsets {magnitude row of the quad's first bin, output band finished by this quad or -1}
+  int mel_qpw;              // quads per warp
+  int vec_ok;               // int16 sources are 8-byte aligned with row strides % 4 == 0
   float* mel_out;           // [S, max_frames, n_mel], or stream-tiled (common.cuh) when tiled_out
   int tiled_out;
-  float mag_scale;          // 0.5 * (int16 input ? 2^-15 : 1)
+  float mag_scale;          // 0.5 * (int16 input ? 2^-15 : 1), applied to the finished band sums
   // fused server pre-step (only with groups == 1 and int16 input): VAD, frame count, next tail
   int fuse_pre;
   long long vad_limit;
@@ -68,37 +80,49 @@ struct FrontendParams {
   int* nframes_out;         // [S]
 };
 
-// Magnitude column ("frame slot") of frame fr of pair p in the transposed [bin][33] array.  Chosen so that the
-// 32 lanes of a warp in the untangle phase (consecutive columns of two adjacent pairs) hit 32 distinct banks:
-// consecutive pairs are 20 slots apart mod 32; the 2 x 16 frames still fill the 32 slots exactly once.
-__device__ __forceinline__ int mag_slot(int pair, int fr) { return ((20 * pair) & 31) + 2 * (pair >> 3) + fr; }
+// Transposed magnitudes: bin k of frame slot sl sits at (k/2)*66 + 2*sl + (k&1), so the mel projection (lane = slot)
+// reads two consecutive bins with one conflict-free 64-bit load.  Frame slot of frame fr of pair p: chosen so that the
+// 32 lanes of a warp in the untangle phase (consecutive columns k2 of adjacent pairs, same k1) hit 32 distinct banks:
+// bank = (k + 2*slot) mod 32 must advance by 20 per pair, i.e. slot = 10*p mod 16; pairs 8..15 take the upper 16
+// slots.  The 2 x 16 frames fill the 32 slots exactly once.
+__device__ __forceinline__ int mag_slot(int pair, int fr) { return ((10 * pair) & 15) + 16 * (pair >> 3) + fr; }
 // inverse: slot -> frame index 2*pair + fr within the item  (5*5 = 25 = 1 mod 8)
 __device__ __forceinline__ int slot_frame(int slot) {
-  const int pair = ((5 * (slot >> 2)) & 7) + 8 * ((slot >> 1) & 1);
+  const int pair = ((5 * ((slot & 15) >> 1)) & 7) + 8 * (slot >> 4);
   return 2 * pair + (slot & 1);
 }
+__device__ __forceinline__ int mag_index(int bin, int slot) { return (bin >> 1) * kFeMagStride + 2 * slot + (bin & 1); }
 
+// four int16 samples of one 8-byte load -> floats (exact)
+__device__ __forceinline__ float4 quad_to_float(uint2 q) {
+  return make_float4(static_cast<float>(static_cast<short>(q.x & 0xffffu)), static_cast<float>(static_cast<int>(q.x) >> 16),
+                     static_cast<float>(static_cast<short>(q.y & 0xffffu)), static_cast<float>(static_cast<int>(q.y) >> 16));
+}
+__device__ __forceinline__ int quad_abs_sum(uint2 q) {
+  return abs(static_cast<int>(static_cast<short>(q.x & 0xffffu))) + abs(static_cast<int>(q.x) >> 16) +
+         abs(static_cast<int>(static_cast<short>(q.y & 0xffffu))) + abs(static_cast<int>(q.y) >> 16);
+}
+
+template <bool kQuadsInSmem>
 __global__ void __launch_bounds__(kFeThreads, 2)
 frontend_kernel(const FrontendParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* twp = reinterpret_cast<cpx*>(smem_raw);                      // [1040]
   cpx* buf = twp + fft::kTwSlots;                                   // [16][420]; later the [32][M] output tile
-  float* win = reinterpret_cast<float*>(buf + kFePairs * fft::kBufSlots);   // window, later magnitudes [201][33]
-  float* mel_w = win + kFeRegionFloats;                             // [nnz]
-  int* mel_start = reinterpret_cast<int*>(mel_w + p.mel_nnz);       // [M]
-  int* mel_count = mel_start + p.n_mel;
-  int* mel_off = mel_count + p.n_mel;
-  int* red = mel_off + p.n_mel;                                     // [16] block reduction scratch
+  float* win = reinterpret_cast<float*>(buf + kFePairs * fft::kBufSlots);   // window, later magnitudes [102][66]
+  int* red = reinterpret_cast<int*>(win + kFeRegionFloats);         // [16] block reduction scratch
+  float4* s_qw = reinterpret_cast<float4*>(red + 16);               // [10][qpw]   (only when kQuadsInSmem)
+  int2* s_qm = reinterpret_cast<int2*>(s_qw + (kQuadsInSmem ? kFeWarps * p.mel_qpw : 0));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < fft::kTwSlots; i += kFeThreads) twp[i] = p.twiddle[i];
-  for (int i = tid; i < p.mel_nnz; i += kFeThreads) mel_w[i] = p.mel_weight[i];
-  for (int i = tid; i < p.n_mel; i += kFeThreads) {
-    mel_start[i] = p.mel_start[i];
-    mel_count[i] = p.mel_count[i];
-    mel_off[i] = p.mel_offset[i];
+  if (kQuadsInSmem) {
+    for (int i = tid; i < kFeWarps * p.mel_qpw; i += kFeThreads) {
+      s_qw[i] = p.mel_qw[i];
+      s_qm[i] = p.mel_qm[i];
+    }
   }
-  for (int i = fft::kBins * kFeMagStride + tid; i < kFeRegionFloats; i += kFeThreads) win[i] = 0.0f;
+  for (int i = kFeMagLive + tid; i < kFeRegionFloats; i += kFeThreads) win[i] = 0.0f;   // bins 201..203 (200 is rewritten)
 
   const int pair = tid / fft::kR;
   const int col = tid - pair * fft::kR;
@@ -109,63 +133,104 @@ frontend_kernel(const FrontendParams p) {
   const long items = p.S * p.groups;
   const bool i16 = p.src.body_dtype == KWS_PCM_I16;
   const int M = p.n_mel;
+  const float4* my_qw = (kQuadsInSmem ? s_qw : p.mel_qw) + warp * p.mel_qpw;
+  const int2* my_qm = (kQuadsInSmem ? s_qm : p.mel_qm) + warp * p.mel_qpw;
   __syncthreads();                                    // tables staged
   // Barriers per item: window staged | Y' exchanged | Z mirror rows published | magnitudes published | mel tile
   // complete.  The next item's staging writes the window/magnitude region (last read before the fifth barrier) and
   // its stage 1 writes `buf` after its own first barrier, so no barrier is needed at the loop boundary.
 
-  for (long item = blockIdx.x; item < items; item += gridDim.x) {
+  // ---- int16 staging, split in two so that the loads of item i+1 are in flight during the mel projection of item i.
+  // Thread t owns the quads of stream samples q0 + 4t + 1280r (r < 5; the fifth round only for t < 60).
+  const bool last_quad_ok = tid < kFeLastQuads;
+  auto load_quads = [&](long item, int head_len, uint2 (&pre)[kFeQuadRounds]) {
+    const long s = item / p.groups;
+    const int q0 = static_cast<int>(item - s * p.groups) * kFeItemHop;
+    const int total_len = head_len + p.src.body_len;
+    // both pointers are indexed by the stream sample number
+    const int16_t* body = static_cast<const int16_t*>(p.src.body) + s * p.src.ld_body - head_len;
+    const int16_t* head = p.src.head + s * p.src.ld_head;             // only dereferenced below head_len
+    const bool vec = p.vec_ok && (head_len & 3) == 0;
+    auto fetch1 = [&](int q) -> unsigned {
+      int x = 0;
+      if (q < head_len) x = head[q];
+      else if (q < total_len) x = body[q];
+      return static_cast<unsigned>(x) & 0xffffu;
+    };
+    auto fetch = [&](int r) {
+      const int q = q0 + 4 * tid + 4 * kFeThreads * r;
+      uint2 v = make_uint2(0u, 0u);
+      if (vec && q >= head_len && q + 4 <= total_len) v = __ldg(reinterpret_cast<const uint2*>(body + q));
+      else if (vec && q + 4 <= head_len) v = *reinterpret_cast<const uint2*>(head + q);
+      else if (q < total_len) v = make_uint2(fetch1(q) | (fetch1(q + 1) << 16), fetch1(q + 2) | (fetch1(q + 3) << 16));
+      return v;
+    };
+    // rounds 1..3 hold samples [q0+1280, q0+5120): entirely inside the chunk for every steady-state item
+    const bool fast = vec && q0 + 4 * kFeThreads >= head_len && q0 + 4 * kFeThreads * (kFeQuadRounds - 1) <= total_len;
+    pre[0] = fetch(0);
+    if (fast) {
+#pragma unroll
+      for (int r = 1; r < kFeQuadRounds - 1; ++r)
+        pre[r] = __ldg(reinterpret_cast<const uint2*>(body + q0 + 4 * tid + 4 * kFeThreads * r));
+    } else {
+#pragma unroll
+      for (int r = 1; r < kFeQuadRounds - 1; ++r) pre[r] = fetch(r);
+    }
+    pre[kFeQuadRounds - 1] = last_quad_ok ? fetch(kFeQuadRounds - 1) : make_uint2(0u, 0u);
+  };
+  // window position of sample i is i + 20*(i/320); for i = 4t + 1280r that is 4t + 1360r + 20*(t/80)
+  float* my_stage = win + 4 * tid + kFeSkew * (tid / (kFeBlock / 4));
+  auto store_quads = [&](int q0, int head_len, const uint2 (&pre)[kFeQuadRounds]) {
+    int acc = 0;
+#pragma unroll
+    for (int r = 0; r < kFeQuadRounds; ++r) {
+      if (r < kFeQuadRounds - 1 || last_quad_ok)
+        *reinterpret_cast<float4*>(my_stage + (4 * kFeThreads + 4 * kFeSkew) * r) = quad_to_float(pre[r]);
+      // VAD over the new samples only (detector.py:168); samples beyond the signal were loaded as zeros
+      const int q = q0 + 4 * tid + 4 * kFeThreads * r;
+      if (!p.fuse_pre) continue;
+      if (q >= head_len) acc += quad_abs_sum(pre[r]);
+      else if (q + 4 > head_len) {
+        const float4 f = quad_to_float(pre[r]);
+        const float e[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (q + j >= head_len) acc += abs(static_cast<int>(e[j]));
+      }
+    }
+    return acc;
+  };
+
+  long item = blockIdx.x;
+  uint2 pre[kFeQuadRounds];
+  int head_len = 0;
+  if (i16 && item < items) {
+    head_len = p.src.head_len ? p.src.head_len[item / p.groups] : 0;
+    load_quads(item, head_len, pre);
+  }
+
+  for (; item < items; item += gridDim.x) {
     const long s = item / p.groups;
     const int g = static_cast<int>(item - s * p.groups);
-    const int head_len = p.src.head_len ? p.src.head_len[s] : 0;
+    if (!i16) head_len = p.src.head_len ? p.src.head_len[s] : 0;
     const int total_len = head_len + p.src.body_len;
     const int nfr_sig = total_len >= kFft ? 1 + (total_len - kFft) / kHop : 0;
     int nfr = p.fuse_pre ? nfr_sig : (p.nframes ? p.nframes[s] : nfr_sig);
     if (nfr > p.max_frames) nfr = p.max_frames;
     const int q0 = g * kFeItemHop;                    // stream sample held at window position 0
     const int f0 = g * kFeItemFrames;
+    // the next item's carried-tail length is needed for its addresses: fetch it a whole item ahead
+    const long next = item + gridDim.x;
+    int head_len_next = 0;
+    if (i16 && next < items && p.src.head_len) head_len_next = p.src.head_len[next / p.groups];
 
     // ---- stage the window: stream samples [q0, q0 + 5360) -> win[i + 20*(i/320)], zero beyond the signal.
-    // Thread t takes samples t + 320*r, so the skewed position is simply t + 340*r; the loads are unit-stride
-    // across the warp and all 17 of a thread are independent (one round trip to HBM).
     int vad_acc = 0;
-    const bool last_ok = tid < kFeWinSamples - kFeBlock * (kFeWinRounds - 1);   // the 17th round is partial
     if (i16) {
-      const int16_t* body = static_cast<const int16_t*>(p.src.body) + s * p.src.ld_body - head_len + q0 + tid;
-      const int16_t* head = p.src.head + s * p.src.ld_head + q0 + tid;          // only dereferenced below head_len
-      // generic element: carried tail, chunk, or zero beyond the signal
-      auto fetch = [&](int r) {
-        const int q = q0 + tid + kFeBlock * r;
-        const bool in_head = q < head_len;
-        const int16_t* ptr = in_head ? head + kFeBlock * r : body + kFeBlock * r;
-        int x = 0;
-        if (q < total_len) x = *ptr;
-        return x;
-      };
-      // rounds 2..14 hold samples [q0+640, q0+4800): entirely inside the chunk for every steady-state item
-      const bool fast = q0 + 2 * kFeBlock >= head_len && q0 + 15 * kFeBlock <= total_len;
-      if (fast) {
-        int x[kFeWinRounds];
-        x[0] = fetch(0);
-        x[1] = fetch(1);
-#pragma unroll
-        for (int r = 2; r < 15; ++r) x[r] = __ldg(body + kFeBlock * r);
-        x[15] = fetch(15);
-        x[16] = last_ok ? fetch(16) : 0;
-#pragma unroll
-        for (int r = 0; r < kFeWinRounds; ++r) {
-          if (r < kFeWinRounds - 1 || last_ok) win[tid + (kFeBlock + kFeSkew) * r] = static_cast<float>(x[r]);
-          if (r >= 2 || q0 + tid + kFeBlock * r >= head_len) vad_acc += abs(x[r]);
-        }
-      } else {
-#pragma unroll 1
-        for (int r = 0; r < kFeWinRounds; ++r) {
-          const int x = (r < kFeWinRounds - 1 || last_ok) ? fetch(r) : 0;
-          if (r < kFeWinRounds - 1 || last_ok) win[tid + (kFeBlock + kFeSkew) * r] = static_cast<float>(x);
-          if (q0 + tid + kFeBlock * r >= head_len) vad_acc += abs(x);
-        }
-      }
+      vad_acc = store_quads(q0, head_len, pre);
     } else {
+      // fp32 PCM: thread t takes samples t + 320*r, so the skewed position is simply t + 340*r
+      const bool last_ok = tid < kFeWinSamples - kFeBlock * (kFeWinRounds - 1);   // the 17th round is partial
       const float* body = static_cast<const float*>(p.src.body) + s * p.src.ld_body + q0 + tid;
 #pragma unroll
       for (int r = 0; r < kFeWinRounds; ++r) {
@@ -214,31 +279,41 @@ frontend_kernel(const FrontendParams p) {
     __syncthreads();
     if (live) fft::stage2_col(col, my_buf, v);
     __syncthreads();
-    // magnitudes, transposed: mag[bin*33 + slot]; the window is dead since the second barrier
+    // magnitudes (times 2, unscaled), transposed (mag_index); the window is dead since the second barrier
     float* mag = win;
-    if (live) fft::untangle_col(col, v, my_buf, p.mag_scale, mag + mag_slot(pair, 0), mag + mag_slot(pair, 1), kFeMagStride);
+    if (live)
+      fft::untangle_col(col, v, my_buf, mag + mag_index(col, mag_slot(pair, 0)), mag + mag_index(col, mag_slot(pair, 1)),
+                        (fft::kR / 2) * kFeMagStride);
     __syncthreads();
-    // ---- mel projection: lane = frame slot, warp = set of bands {warp, warp+10, ...}: band ranges and weights
-    // are warp-uniform (broadcast reads, no divergence), magnitude reads are unit-stride across the lanes
+    // ---- the next item's PCM: loads in flight during the mel projection and the output copy
+    if (i16 && next < items) load_quads(next, head_len_next, pre);
+    // ---- mel projection: lane = frame slot; the warp walks its own flat list of quads (whole bands, dealt out at
+    // model creation so that all warps carry the same number of quads).  Weights, row offsets and band ends are
+    // warp-uniform broadcast reads; magnitude reads are unit-stride across the lanes; no divergence, no inner loop.
     {
-      const int fi = slot_frame(lane);
-      const float* mcol = mag + lane;
-      for (int m = warp; m < M; m += kFeWarps) {
-        const int k0 = mel_start[m], c = mel_count[m];
-        const float* wv = mel_w + mel_off[m];
-        const float* mp = mcol + k0 * kFeMagStride;
-        // ranges are padded to a multiple of 4 bins with zero weights (api.cu); the rows past bin 200 are zero
-        float acc0 = 0.0f, acc1 = 0.0f;
-        for (int i = 0; i < c; i += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wv + i);
-          acc0 = fmaf(mp[0], w4.x, acc0);
-          acc1 = fmaf(mp[kFeMagStride], w4.y, acc1);
-          acc0 = fmaf(mp[2 * kFeMagStride], w4.z, acc0);
-          acc1 = fmaf(mp[3 * kFeMagStride], w4.w, acc1);
-          mp += 4 * kFeMagStride;
+      char* orow = reinterpret_cast<char*>(out_tile + slot_frame(lane) * M);
+      const char* mcol = reinterpret_cast<const char*>(mag + 2 * lane);
+      const float scale = p.mag_scale;
+      float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+      for (int q = 0; q < p.mel_qpw; ++q) {
+        float4 w4;
+        int2 me;                                        // byte offsets: magnitude row pair, output band (or < 0)
+        if (kQuadsInSmem) {
+          w4 = my_qw[q];
+          me = my_qm[q];
+        } else {
+          w4 = __ldg(my_qw + q);
+          me = __ldg(my_qm + q);
         }
-        const float acc = acc0 + acc1;
-        out_tile[fi * M + m] = acc;
+        const float2 m01 = *reinterpret_cast<const float2*>(mcol + me.x);
+        const float2 m23 = *reinterpret_cast<const float2*>(mcol + me.x + kFeMagStride * sizeof(float));
+        acc = __ffma2_rn(m01, make_float2(w4.x, w4.y), acc);
+        acc = __ffma2_rn(m23, make_float2(w4.z, w4.w), acc);
+        const bool band_end = me.y >= 0;
+        if (band_end) *reinterpret_cast<float*>(orow + me.y) = (acc.x + acc.y) * scale;
+        acc.x = band_end ? 0.0f : acc.x;
+        acc.y = band_end ? 0.0f : acc.y;
       }
     }
     __syncthreads();
@@ -264,12 +339,60 @@ frontend_kernel(const FrontendParams p) {
         }
       }
     }
+    head_len = head_len_next;
   }
 }
 
+// Cut the non-zero part of the mel basis [201, M] into quads and deal whole bands to the kFeWarps warps of the
+// front-end CTA, longest band first onto the least loaded warp, padding every warp's list to the same length with
+// all-zero quads.  quad_w[w*qpw + q] = 4 weights of bins k..k+3 (k even) of one band; quad_m[..] = {byte offset of
+// magnitude row k/2, byte offset of the band whose sum is complete after this quad or -1}.  Zeros of the basis contribute nothing, so this is exact for any basis.
+void build_mel_quads(const float* basis, int M, std::vector<float4>* quad_w, std::vector<int2>* quad_m, int* quads_per_warp) {
+  struct Band { int b, lo, nq; };
+  std::vector<Band> bands;
+  for (int b = 0; b < M; ++b) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < kBins; ++k)
+      if (basis[static_cast<size_t>(k) * M + b] != 0.0f) {
+        if (lo < 0) lo = k;
+        hi = k;
+      }
+    if (lo < 0) lo = hi = 0;                               // empty band: one zero quad still writes its 0
+    lo &= ~1;                                              // quads start at an even bin (64-bit magnitude reads)
+    bands.push_back(Band{b, lo, (hi - lo + 1 + 3) / 4});
+  }
+  std::stable_sort(bands.begin(), bands.end(), [](const Band& x, const Band& y) { return x.nq > y.nq; });
+  std::vector<std::vector<Band>> per_warp(kFeWarps);
+  std::vector<int> load(kFeWarps, 0);
+  for (const Band& bd : bands) {
+    const int w = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+    per_warp[w].push_back(bd);
+    load[w] += bd.nq;
+  }
+  const int qpw = std::max(1, *std::max_element(load.begin(), load.end()));
+  quad_w->assign(static_cast<size_t>(kFeWarps) * qpw, make_float4(0.f, 0.f, 0.f, 0.f));
+  quad_m->assign(static_cast<size_t>(kFeWarps) * qpw, make_int2(0, -1));
+  for (int w = 0; w < kFeWarps; ++w) {
+    size_t at = static_cast<size_t>(w) * qpw;
+    for (const Band& bd : per_warp[w])
+      for (int j = 0; j < bd.nq; ++j, ++at) {
+        float wv[4];
+        for (int e = 0; e < 4; ++e) {
+          const int k = bd.lo + 4 * j + e;                 // rows 201..203 of the magnitude array are zero
+          wv[e] = k < kBins ? basis[static_cast<size_t>(k) * M + bd.b] : 0.0f;
+        }
+        (*quad_w)[at] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        (*quad_m)[at] = make_int2(((bd.lo + 4 * j) / 2) * kFeMagStride * static_cast<int>(sizeof(float)),
+                                  j == bd.nq - 1 ? bd.b * static_cast<int>(sizeof(float)) : -1);
+      }
+  }
+  *quads_per_warp = qpw;
+}
+
+static bool quads_in_smem(const kws_model* m) { return kFeWarps * m->mel.quads_per_warp <= kFeQuadSmemMax; }
 static size_t frontend_smem_bytes(const kws_model* m) {
   return sizeof(cpx) * fft::kTwSlots + sizeof(cpx) * kFePairs * fft::kBufSlots + sizeof(float) * kFeRegionFloats +
-         sizeof(float) * m->mel.nnz + sizeof(int) * 3 * m->cfg.n_mel + sizeof(int) * 16;
+         sizeof(int) * 16 + (quads_in_smem(m) ? (sizeof(float4) + sizeof(int2)) * kFeWarps * m->mel.quads_per_warp : 0);
 }
 
 bool frontend_can_fuse_pre(int chunk_len, int tail_cap) {
@@ -288,11 +411,11 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
   p.nframes = nframes;
   p.n_mel = m->cfg.n_mel;
   p.twiddle = reinterpret_cast<const cpx*>(m->twiddle400);
-  p.mel_start = m->mel.start;
-  p.mel_count = m->mel.count;
-  p.mel_offset = m->mel.offset;
-  p.mel_weight = m->mel.weight;
-  p.mel_nnz = m->mel.nnz;
+  p.mel_qw = m->mel.quad_w;
+  p.mel_qm = m->mel.quad_m;
+  p.mel_qpw = m->mel.quads_per_warp;
+  p.vec_ok = (reinterpret_cast<uintptr_t>(src.body) % 8 == 0 && src.ld_body % 4 == 0 &&
+              reinterpret_cast<uintptr_t>(src.head) % 8 == 0 && src.ld_head % 4 == 0) ? 1 : 0;
   p.mel_out = mel_out;
   p.tiled_out = tiled_out ? 1 : 0;
   if (tiled_out && (m->cfg.n_mel & 3)) return fail(KWS_ERR_INVALID_ARGUMENT, "tiled mel output needs n_mel % 4 == 0");
@@ -313,21 +436,22 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
     p.silence = pre->silence;
     p.nframes_out = pre->nframes_out;
   }
+  const bool in_smem = quads_in_smem(m);
+  auto kernel = in_smem ? frontend_kernel<true> : frontend_kernel<false>;
   const size_t smem = frontend_smem_bytes(m);
-  static thread_local size_t configured = 0;
-  if (configured < smem) {
-    KWS_CUDA_OK(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-    configured = smem;
+  static thread_local size_t configured[2] = {0, 0};
+  if (configured[in_smem] < smem) {
+    KWS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured[in_smem] = smem;
   }
   int per_sm = 0;
-  KWS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel, kFeThreads, smem));
+  KWS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFeThreads, smem));
   if (per_sm < 1) return fail(KWS_ERR_CUDA, "frontend_kernel does not fit on an SM (smem %zu)", smem);
   const long items = S * p.groups;
   long blocks = items;
   const long resident = static_cast<long>(per_sm) * sm_count();
   if (blocks > resident) blocks = resident;
-  frontend_kernel<<<static_cast<unsigned>(blocks), kFeThreads, smem, st>>>(p);
+  kernel<<<static_cast<unsigned>(blocks), kFeThreads, smem, st>>>(p);
   KWS_LAUNCH_OK("frontend_kernel");
   return KWS_OK;
 }

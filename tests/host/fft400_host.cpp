@@ -29,7 +29,8 @@ extern "C" void fft400_pair_mags(const float* win560, float* mag_a201, float* ma
     stage1_col(c, regs[c], twp + tw_base(t >> 5, t & 31), buf);
   }                                                  // --- barrier ---
   for (int c = 0; c < kR; ++c) stage2_col(c, buf, regs[c]);   // --- barrier ---
-  for (int c = kR - 1; c >= 0; --c) untangle_col(c, regs[c], buf, 0.5f, mag_a201, mag_b201, 1);
+  for (int c = kR - 1; c >= 0; --c) untangle_col(c, regs[c], buf, mag_a201 + c, mag_b201 + c, kR);   // 2|A|, 2|B|
+  for (int k = 0; k < kBins; ++k) { mag_a201[k] *= 0.5f; mag_b201[k] *= 0.5f; }
 }
 
 extern "C" void dft20_host(const float* in40, float* out40) {

@@ -133,6 +133,7 @@ frontend_kernel(const FrontendParams p) {
   const long items = p.S * p.groups;
   const bool i16 = p.src.body_dtype == KWS_PCM_I16;
   const int M = p.n_mel;
+  const int Mp = M | 1;                               // odd row stride of the [32][M] output tile: conflict-free band writes
   const float4* my_qw = (kQuadsInSmem ? s_qw : p.mel_qw) + warp * p.mel_qpw;
   const int2* my_qm = (kQuadsInSmem ? s_qm : p.mel_qm) + warp * p.mel_qpw;
   __syncthreads();                                    // tables staged
@@ -291,7 +292,7 @@ frontend_kernel(const FrontendParams p) {
     // model creation so that all warps carry the same number of quads).  Weights, row offsets and band ends are
     // warp-uniform broadcast reads; magnitude reads are unit-stride across the lanes; no divergence, no inner loop.
     {
-      char* orow = reinterpret_cast<char*>(out_tile + slot_frame(lane) * M);
+      char* orow = reinterpret_cast<char*>(out_tile + slot_frame(lane) * Mp);
       const char* mcol = reinterpret_cast<const char*>(mag + 2 * lane);
       const float scale = p.mag_scale;
       float2 acc = make_float2(0.0f, 0.0f);
@@ -322,20 +323,28 @@ frontend_kernel(const FrontendParams p) {
       int nfi = nfr - f0;
       if (nfi > kFeItemFrames) nfi = kFeItemFrames;
       const int total = nfi > 0 ? nfi * M : 0;
-      if (p.tiled_out) {
-        // float4 chunk c of frame f -> ((tile*n + f)*Q + c)*128 + stream%128
+      if ((M & 3) == 0 && (p.tiled_out || (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0)) {
+        // 16-byte pieces: chunk c (of Q) of frame f goes to row-major (s*n + f0 + f)*Q + c or, stream-tiled, to
+        // ((tile*n + f0 + f)*Q + c)*128 + stream%128
         const int Q = M >> 2;
-        const float4* src4 = reinterpret_cast<const float4*>(out_tile);
-        float4* dst4 = reinterpret_cast<float4*>(p.mel_out) + ((s >> 7) * p.max_frames + f0) * static_cast<long>(Q) * 128 + (s & 127);
-        for (int i = tid; i < (total >> 2); i += kFeThreads) dst4[static_cast<long>(i) * 128] = src4[i];
+        float4* dst4 = reinterpret_cast<float4*>(p.mel_out);
+        long step = 1;
+        if (p.tiled_out) {
+          dst4 += ((s >> 7) * p.max_frames + f0) * static_cast<long>(Q) * 128 + (s & 127);
+          step = 128;
+        } else {
+          dst4 += (s * p.max_frames + f0) * static_cast<long>(Q);
+        }
+        for (int i = tid; i < (total >> 2); i += kFeThreads) {
+          const int f = i / Q, c = i - f * Q;
+          const float* src = out_tile + f * Mp + 4 * c;
+          dst4[i * step] = make_float4(src[0], src[1], src[2], src[3]);
+        }
       } else {
         float* dst = p.mel_out + (s * p.max_frames + f0) * M;
-        if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0) {
-          const float4* src4 = reinterpret_cast<const float4*>(out_tile);
-          float4* dst4 = reinterpret_cast<float4*>(dst);
-          for (int i = tid; i < (total >> 2); i += kFeThreads) dst4[i] = src4[i];
-        } else {
-          for (int i = tid; i < total; i += kFeThreads) dst[i] = out_tile[i];
+        for (int i = tid; i < total; i += kFeThreads) {
+          const int f = i / M;
+          dst[i] = out_tile[f * Mp + (i - f * M)];
         }
       }
     }

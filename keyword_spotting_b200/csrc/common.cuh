@@ -64,9 +64,14 @@ struct LayerWeights {
   float* tc_bias = nullptr;
 };
 
-struct MelSparse {               // non-zero part of the mel basis as per-warp lists of 4-bin quads (frontend.cu)
-  float4* quad_w = nullptr;      // [10 warps][quads_per_warp] weights
-  int2* quad_m = nullptr;        // [10 warps][quads_per_warp] {magnitude row offset, finished band or -1}
+struct alignas(16) MelQuad {     // 4 consecutive bins (from an even bin) of one mel band
+  float w[4];
+  int mag_off;                   // byte offset of the bin pair's row in the front end's transposed magnitude array
+  int band_off;                  // byte offset of the band in the output row if this quad completes it, else -1
+  int pad[2];
+};
+struct MelSparse {               // non-zero part of the mel basis as per-warp lists of quads (frontend.cu)
+  MelQuad* quads = nullptr;      // [10 warps][quads_per_warp]
   int quads_per_warp = 0;
 };
 
@@ -115,8 +120,7 @@ struct FrontendPre {
   int32_t* nframes_out = nullptr;     // [S]
 };
 bool frontend_can_fuse_pre(int chunk_len, int tail_cap);
-void build_mel_quads(const float* basis /*[201, M] host*/, int M, std::vector<float4>* quad_w, std::vector<int2>* quad_m,
-                     int* quads_per_warp);
+void build_mel_quads(const float* basis /*[201, M] host*/, int M, std::vector<MelQuad>* quads, int* quads_per_warp);
 // Stream-tiled mel scratch (front end -> tensor-core GRU): float4 chunk c (of Q = M/4) of frame t of stream s sits at
 // float4 index ((s/128 * n + t) * Q + c) * 128 + s % 128, so the 128 threads of a GRU tile read, and the front end
 // writes, 16-byte pieces that are contiguous across streams.  Size: ceil(S/128)*128 * n * M floats.

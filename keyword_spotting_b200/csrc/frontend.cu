@@ -44,7 +44,7 @@ constexpr int kFeWinRounds = (kFeWinSamples + kFeThreads - 1) / kFeThreads;   //
 constexpr int kFeQuadRounds = (kFeWinSamples + 4 * kFeThreads - 1) / (4 * kFeThreads);      // 5 (int16: 4 samples per load)
 constexpr int kFeLastQuads = (kFeWinSamples - 4 * kFeThreads * (kFeQuadRounds - 1)) / 4;    // 60 threads in the last round
 static_assert(kFeWinSamples % 4 == 0 && kFeBlock % 4 == 0, "quads must not straddle a skew boundary");
-constexpr int kFeQuadSmemMax = 1536;                 // quads kept in shared memory (24 B each); more -> read from global
+constexpr int kFeQuadSmemMax = 512;                  // quads kept in shared memory (32 B each, keeps 2 CTAs per SM); more -> read from global
 constexpr int kFeItemHop = kFePairs * kFeBlock;      // 5120 samples between consecutive items of a stream
 constexpr int kFeMagStride = 66;                     // floats per row of the transposed magnitudes [102 bin pairs][32 slots][2] (+2 pad)
 // the window (5360 samples + skew) and the transposed magnitudes share one region: the window is dead after stage 1
@@ -64,9 +64,8 @@ struct FrontendParams {
   const int* nframes;       // [S] or null -> frames from the signal length
   int n_mel;
   const cpx* twiddle;       // [20*52] periodic k2-major table (fft::kTwSlots)
-  const float4* mel_qw;     // [10 warps][quads_per_warp] weights of 4 consecutive bins
-  const int2* mel_qm;       // same shape: byte offsets {magnitude row of the quad's first bin, output band finished by this quad or -1}
-  int mel_qpw;              // quads per warp
+  const MelQuad* mel_q;     // [10 warps][quads_per_warp] (common.cuh)
+  int mel_qpw;              // quads per warp (even)
   int vec_ok;               // int16 sources are 8-byte aligned with row strides % 4 == 0
   float* mel_out;           // [S, max_frames, n_mel], or stream-tiled (common.cuh) when tiled_out
   int tiled_out;
@@ -98,11 +97,6 @@ __device__ __forceinline__ float4 quad_to_float(uint2 q) {
   return make_float4(static_cast<float>(static_cast<short>(q.x & 0xffffu)), static_cast<float>(static_cast<int>(q.x) >> 16),
                      static_cast<float>(static_cast<short>(q.y & 0xffffu)), static_cast<float>(static_cast<int>(q.y) >> 16));
 }
-__device__ __forceinline__ int quad_abs_sum(uint2 q) {
-  return abs(static_cast<int>(static_cast<short>(q.x & 0xffffu))) + abs(static_cast<int>(q.x) >> 16) +
-         abs(static_cast<int>(static_cast<short>(q.y & 0xffffu))) + abs(static_cast<int>(q.y) >> 16);
-}
-
 template <bool kQuadsInSmem>
 __global__ void __launch_bounds__(kFeThreads, 2)
 frontend_kernel(const FrontendParams p) {
@@ -111,16 +105,13 @@ frontend_kernel(const FrontendParams p) {
   cpx* buf = twp + fft::kTwSlots;                                   // [16][420]; later the [32][M] output tile
   float* win = reinterpret_cast<float*>(buf + kFePairs * fft::kBufSlots);   // window, later magnitudes [102][66]
   int* red = reinterpret_cast<int*>(win + kFeRegionFloats);         // [16] block reduction scratch
-  float4* s_qw = reinterpret_cast<float4*>(red + 16);               // [10][qpw]   (only when kQuadsInSmem)
-  int2* s_qm = reinterpret_cast<int2*>(s_qw + (kQuadsInSmem ? kFeWarps * p.mel_qpw : 0));
+  MelQuad* s_q = reinterpret_cast<MelQuad*>(red + 16);              // [10][qpw]   (only when kQuadsInSmem)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < fft::kTwSlots; i += kFeThreads) twp[i] = p.twiddle[i];
   if (kQuadsInSmem) {
-    for (int i = tid; i < kFeWarps * p.mel_qpw; i += kFeThreads) {
-      s_qw[i] = p.mel_qw[i];
-      s_qm[i] = p.mel_qm[i];
-    }
+    const int n16 = kFeWarps * p.mel_qpw * static_cast<int>(sizeof(MelQuad) / 16);
+    for (int i = tid; i < n16; i += kFeThreads) reinterpret_cast<uint4*>(s_q)[i] = reinterpret_cast<const uint4*>(p.mel_q)[i];
   }
   for (int i = kFeMagLive + tid; i < kFeRegionFloats; i += kFeThreads) win[i] = 0.0f;   // bins 201..203 (200 is rewritten)
 
@@ -134,8 +125,7 @@ frontend_kernel(const FrontendParams p) {
   const bool i16 = p.src.body_dtype == KWS_PCM_I16;
   const int M = p.n_mel;
   const int Mp = M | 1;                               // odd row stride of the [32][M] output tile: conflict-free band writes
-  const float4* my_qw = (kQuadsInSmem ? s_qw : p.mel_qw) + warp * p.mel_qpw;
-  const int2* my_qm = (kQuadsInSmem ? s_qm : p.mel_qm) + warp * p.mel_qpw;
+  const MelQuad* my_q = (kQuadsInSmem ? s_q : p.mel_q) + warp * p.mel_qpw;
   __syncthreads();                                    // tables staged
   // Barriers per item: window staged | Y' exchanged | Z mirror rows published | magnitudes published | mel tile
   // complete.  The next item's staging writes the window/magnitude region (last read before the fifth barrier) and
@@ -151,55 +141,60 @@ frontend_kernel(const FrontendParams p) {
     // both pointers are indexed by the stream sample number
     const int16_t* body = static_cast<const int16_t*>(p.src.body) + s * p.src.ld_body - head_len;
     const int16_t* head = p.src.head + s * p.src.ld_head;             // only dereferenced below head_len
-    const bool vec = p.vec_ok && (head_len & 3) == 0;
-    auto fetch1 = [&](int q) -> unsigned {
-      int x = 0;
-      if (q < head_len) x = head[q];
-      else if (q < total_len) x = body[q];
-      return static_cast<unsigned>(x) & 0xffffu;
-    };
-    auto fetch = [&](int r) {
-      const int q = q0 + 4 * tid + 4 * kFeThreads * r;
-      uint2 v = make_uint2(0u, 0u);
-      if (vec && q >= head_len && q + 4 <= total_len) v = __ldg(reinterpret_cast<const uint2*>(body + q));
-      else if (vec && q + 4 <= head_len) v = *reinterpret_cast<const uint2*>(head + q);
-      else if (q < total_len) v = make_uint2(fetch1(q) | (fetch1(q + 1) << 16), fetch1(q + 2) | (fetch1(q + 3) << 16));
-      return v;
-    };
-    // rounds 1..3 hold samples [q0+1280, q0+5120): entirely inside the chunk for every steady-state item
-    const bool fast = vec && q0 + 4 * kFeThreads >= head_len && q0 + 4 * kFeThreads * (kFeQuadRounds - 1) <= total_len;
-    pre[0] = fetch(0);
-    if (fast) {
+    if (p.vec_ok && ((head_len | total_len) & 3) == 0) {
+      // every quad lies entirely in the carried tail, in the chunk, or beyond the signal: one predicated 8-byte load
 #pragma unroll
-      for (int r = 1; r < kFeQuadRounds - 1; ++r)
-        pre[r] = __ldg(reinterpret_cast<const uint2*>(body + q0 + 4 * tid + 4 * kFeThreads * r));
-    } else {
-#pragma unroll
-      for (int r = 1; r < kFeQuadRounds - 1; ++r) pre[r] = fetch(r);
-    }
-    pre[kFeQuadRounds - 1] = last_quad_ok ? fetch(kFeQuadRounds - 1) : make_uint2(0u, 0u);
-  };
-  // window position of sample i is i + 20*(i/320); for i = 4t + 1280r that is 4t + 1360r + 20*(t/80)
-  float* my_stage = win + 4 * tid + kFeSkew * (tid / (kFeBlock / 4));
-  auto store_quads = [&](int q0, int head_len, const uint2 (&pre)[kFeQuadRounds]) {
-    int acc = 0;
-#pragma unroll
-    for (int r = 0; r < kFeQuadRounds; ++r) {
-      if (r < kFeQuadRounds - 1 || last_quad_ok)
-        *reinterpret_cast<float4*>(my_stage + (4 * kFeThreads + 4 * kFeSkew) * r) = quad_to_float(pre[r]);
-      // VAD over the new samples only (detector.py:168); samples beyond the signal were loaded as zeros
-      const int q = q0 + 4 * tid + 4 * kFeThreads * r;
-      if (!p.fuse_pre) continue;
-      if (q >= head_len) acc += quad_abs_sum(pre[r]);
-      else if (q + 4 > head_len) {
-        const float4 f = quad_to_float(pre[r]);
-        const float e[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (q + j >= head_len) acc += abs(static_cast<int>(e[j]));
+      for (int r = 0; r < kFeQuadRounds; ++r) {
+        const int q = q0 + 4 * tid + 4 * kFeThreads * r;
+        const int16_t* src = (q < head_len ? head : body) + q;
+        uint2 v = make_uint2(0u, 0u);
+        if (q < total_len && (r < kFeQuadRounds - 1 || last_quad_ok)) v = __ldg(reinterpret_cast<const uint2*>(src));
+        pre[r] = v;
+      }
+    } else {                                                          // odd lengths / unaligned rows: element by element
+      auto fetch1 = [&](int q) -> unsigned {
+        int x = 0;
+        if (q < head_len) x = head[q];
+        else if (q < total_len) x = body[q];
+        return static_cast<unsigned>(x) & 0xffffu;
+      };
+#pragma unroll 1
+      for (int r = 0; r < kFeQuadRounds; ++r) {
+        const int q = q0 + 4 * tid + 4 * kFeThreads * r;
+        uint2 v = make_uint2(0u, 0u);
+        if (q < total_len && (r < kFeQuadRounds - 1 || last_quad_ok))
+          v = make_uint2(fetch1(q) | (fetch1(q + 1) << 16), fetch1(q + 2) | (fetch1(q + 3) << 16));
+        // (no dynamic register indexing: the loop is not unrolled)
+        if (r == 0) pre[0] = v;
+        if (r == 1) pre[1] = v;
+        if (r == 2) pre[2] = v;
+        if (r == 3) pre[3] = v;
+        if (r == 4) pre[4] = v;
       }
     }
-    return acc;
+  };
+  static_assert(kFeQuadRounds == 5, "load_quads' element-wise path names the rounds");
+  // window position of sample i is i + 20*(i/320); for i = 4t + 1280r that is 4t + 1360r + 20*(t/80)
+  float* my_stage = win + 4 * tid + kFeSkew * (tid / (kFeBlock / 4));
+  // returns the thread's sum of |x| over the NEW samples (detector.py:168), exact in fp32 (<= 20 * 32768); samples
+  // beyond the signal were loaded as zeros
+  auto store_quads = [&](int q0, int head_len, const uint2 (&pre)[kFeQuadRounds]) {
+    float acc = 0.0f;
+    const bool quad_split = (head_len & 3) != 0;                      // a quad may straddle the tail/chunk boundary
+#pragma unroll
+    for (int r = 0; r < kFeQuadRounds; ++r) {
+      const float4 f = quad_to_float(pre[r]);
+      if (r < kFeQuadRounds - 1 || last_quad_ok) *reinterpret_cast<float4*>(my_stage + (4 * kFeThreads + 4 * kFeSkew) * r) = f;
+      const int q = q0 + 4 * tid + 4 * kFeThreads * r;
+      if (!quad_split) {
+        const float a = (fabsf(f.x) + fabsf(f.y)) + (fabsf(f.z) + fabsf(f.w));
+        acc += q >= head_len ? a : 0.0f;
+      } else {
+        acc += (q >= head_len ? fabsf(f.x) : 0.0f) + (q + 1 >= head_len ? fabsf(f.y) : 0.0f) +
+               (q + 2 >= head_len ? fabsf(f.z) : 0.0f) + (q + 3 >= head_len ? fabsf(f.w) : 0.0f);
+      }
+    }
+    return static_cast<int>(acc);
   };
 
   long item = blockIdx.x;
@@ -295,26 +290,37 @@ frontend_kernel(const FrontendParams p) {
       char* orow = reinterpret_cast<char*>(out_tile + slot_frame(lane) * Mp);
       const char* mcol = reinterpret_cast<const char*>(mag + 2 * lane);
       const float scale = p.mag_scale;
+      const MelQuad* rec = my_q;
       float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll 2
-      for (int q = 0; q < p.mel_qpw; ++q) {
-        float4 w4;
-        int2 me;                                        // byte offsets: magnitude row pair, output band (or < 0)
+      auto fetch = [&](const MelQuad* r, float4& w4, int2& me) {
         if (kQuadsInSmem) {
-          w4 = my_qw[q];
-          me = my_qm[q];
+          w4 = *reinterpret_cast<const float4*>(r->w);
+          me = *reinterpret_cast<const int2*>(&r->mag_off);
         } else {
-          w4 = __ldg(my_qw + q);
-          me = __ldg(my_qm + q);
+          w4 = __ldg(reinterpret_cast<const float4*>(r->w));
+          me = __ldg(reinterpret_cast<const int2*>(&r->mag_off));
         }
-        const float2 m01 = *reinterpret_cast<const float2*>(mcol + me.x);
-        const float2 m23 = *reinterpret_cast<const float2*>(mcol + me.x + kFeMagStride * sizeof(float));
+      };
+      auto apply = [&](const float4& w4, const int2& me, const float2& m01, const float2& m23) {
         acc = __ffma2_rn(m01, make_float2(w4.x, w4.y), acc);
         acc = __ffma2_rn(m23, make_float2(w4.z, w4.w), acc);
-        const bool band_end = me.y >= 0;
-        if (band_end) *reinterpret_cast<float*>(orow + me.y) = (acc.x + acc.y) * scale;
-        acc.x = band_end ? 0.0f : acc.x;
-        acc.y = band_end ? 0.0f : acc.y;
+        if (me.y >= 0) {                                // band complete (predicated, warp-uniform)
+          *reinterpret_cast<float*>(orow + me.y) = (acc.x + acc.y) * scale;
+          acc = make_float2(0.0f, 0.0f);
+        }
+      };
+#pragma unroll 1
+      for (int q = p.mel_qpw; q > 0; q -= 2, rec += 2) {  // two quads per trip, all loads of both issued first
+        float4 wa, wb;
+        int2 ma, mb;
+        fetch(rec, wa, ma);
+        fetch(rec + 1, wb, mb);
+        const float2 a01 = *reinterpret_cast<const float2*>(mcol + ma.x);
+        const float2 a23 = *reinterpret_cast<const float2*>(mcol + ma.x + kFeMagStride * sizeof(float));
+        const float2 b01 = *reinterpret_cast<const float2*>(mcol + mb.x);
+        const float2 b23 = *reinterpret_cast<const float2*>(mcol + mb.x + kFeMagStride * sizeof(float));
+        apply(wa, ma, a01, a23);
+        apply(wb, mb, b01, b23);
       }
     }
     __syncthreads();
@@ -354,9 +360,9 @@ frontend_kernel(const FrontendParams p) {
 
 // Cut the non-zero part of the mel basis [201, M] into quads and deal whole bands to the kFeWarps warps of the
 // front-end CTA, longest band first onto the least loaded warp, padding every warp's list to the same length with
-// all-zero quads.  quad_w[w*qpw + q] = 4 weights of bins k..k+3 (k even) of one band; quad_m[..] = {byte offset of
-// magnitude row k/2, byte offset of the band whose sum is complete after this quad or -1}.  Zeros of the basis contribute nothing, so this is exact for any basis.
-void build_mel_quads(const float* basis, int M, std::vector<float4>* quad_w, std::vector<int2>* quad_m, int* quads_per_warp) {
+// all-zero quads (MelQuad, common.cuh: 4 weights of bins k..k+3 (k even) of one band, the byte offset of
+// magnitude row k/2, and the byte offset of the band whose sum is complete after this quad or -1).  Zeros of the basis contribute nothing, so this is exact for any basis.
+void build_mel_quads(const float* basis, int M, std::vector<MelQuad>* quads, int* quads_per_warp) {
   struct Band { int b, lo, nq; };
   std::vector<Band> bands;
   for (int b = 0; b < M; ++b) {
@@ -378,21 +384,24 @@ void build_mel_quads(const float* basis, int M, std::vector<float4>* quad_w, std
     per_warp[w].push_back(bd);
     load[w] += bd.nq;
   }
-  const int qpw = std::max(1, *std::max_element(load.begin(), load.end()));
-  quad_w->assign(static_cast<size_t>(kFeWarps) * qpw, make_float4(0.f, 0.f, 0.f, 0.f));
-  quad_m->assign(static_cast<size_t>(kFeWarps) * qpw, make_int2(0, -1));
+  const int qpw = (std::max(1, *std::max_element(load.begin(), load.end())) + 1) & ~1;   // even: two quads per loop trip
+  MelQuad zero;
+  zero.w[0] = zero.w[1] = zero.w[2] = zero.w[3] = 0.0f;
+  zero.mag_off = 0;
+  zero.band_off = -1;
+  zero.pad[0] = zero.pad[1] = 0;
+  quads->assign(static_cast<size_t>(kFeWarps) * qpw, zero);
   for (int w = 0; w < kFeWarps; ++w) {
     size_t at = static_cast<size_t>(w) * qpw;
     for (const Band& bd : per_warp[w])
       for (int j = 0; j < bd.nq; ++j, ++at) {
-        float wv[4];
+        MelQuad& q = (*quads)[at];
         for (int e = 0; e < 4; ++e) {
-          const int k = bd.lo + 4 * j + e;                 // rows 201..203 of the magnitude array are zero
-          wv[e] = k < kBins ? basis[static_cast<size_t>(k) * M + bd.b] : 0.0f;
+          const int k = bd.lo + 4 * j + e;                 // bins 201..203 of the magnitude array are zero
+          q.w[e] = k < kBins ? basis[static_cast<size_t>(k) * M + bd.b] : 0.0f;
         }
-        (*quad_w)[at] = make_float4(wv[0], wv[1], wv[2], wv[3]);
-        (*quad_m)[at] = make_int2(((bd.lo + 4 * j) / 2) * kFeMagStride * static_cast<int>(sizeof(float)),
-                                  j == bd.nq - 1 ? bd.b * static_cast<int>(sizeof(float)) : -1);
+        q.mag_off = ((bd.lo + 4 * j) / 2) * kFeMagStride * static_cast<int>(sizeof(float));
+        q.band_off = j == bd.nq - 1 ? bd.b * static_cast<int>(sizeof(float)) : -1;
       }
   }
   *quads_per_warp = qpw;
@@ -401,7 +410,7 @@ void build_mel_quads(const float* basis, int M, std::vector<float4>* quad_w, std
 static bool quads_in_smem(const kws_model* m) { return kFeWarps * m->mel.quads_per_warp <= kFeQuadSmemMax; }
 static size_t frontend_smem_bytes(const kws_model* m) {
   return sizeof(cpx) * fft::kTwSlots + sizeof(cpx) * kFePairs * fft::kBufSlots + sizeof(float) * kFeRegionFloats +
-         sizeof(int) * 16 + (quads_in_smem(m) ? (sizeof(float4) + sizeof(int2)) * kFeWarps * m->mel.quads_per_warp : 0);
+         sizeof(int) * 16 + (quads_in_smem(m) ? sizeof(MelQuad) * kFeWarps * m->mel.quads_per_warp : 0);
 }
 
 bool frontend_can_fuse_pre(int chunk_len, int tail_cap) {
@@ -420,8 +429,7 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
   p.nframes = nframes;
   p.n_mel = m->cfg.n_mel;
   p.twiddle = reinterpret_cast<const cpx*>(m->twiddle400);
-  p.mel_qw = m->mel.quad_w;
-  p.mel_qm = m->mel.quad_m;
+  p.mel_q = m->mel.quads;
   p.mel_qpw = m->mel.quads_per_warp;
   p.vec_ok = (reinterpret_cast<uintptr_t>(src.body) % 8 == 0 && src.ld_body % 4 == 0 &&
               reinterpret_cast<uintptr_t>(src.head) % 8 == 0 && src.ld_head % 4 == 0) ? 1 : 0;

@@ -74,8 +74,7 @@ struct GruTcParams {
   float* probs;                // [S, n, C]
   float* logits;               // [S, n, C] or null
   int timeline;                // record g_tc_timeline (debug)
-  // FC weights [128][8] + bias [8] by value: they sit in the constant bank, so the FC FMAs take them as
-  // (uniform) constant operands instead of 2 LDS.128 per hidden unit
+  // FC weights [128][8] + bias [8] by value (copied to shared memory by the last layer's CTAs)
   float fcw[kHidden * kTcMaxClasses];
   float fcb[kTcMaxClasses];
 };
@@ -183,7 +182,8 @@ gru_tc_kernel(const GruTcParams p) {
   unsigned char* sW = smem;                                                         // [384, ktot] fp16
   float* sBias = reinterpret_cast<float*>(smem + static_cast<size_t>(384) * ktot * 2);   // [384] pre-scaled
   float* sXch = sBias + 384;                                               // [3][128][8] FC partials of unit blocks 1..3
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 3 * kTcTile * kTcMaxClasses); // [kNumBars]
+  float* sFc = sXch + 3 * kTcTile * kTcMaxClasses;                         // [128][8] FC weights (last layer)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sFc + kHidden * kTcMaxClasses);     // [kNumBars]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -205,6 +205,8 @@ gru_tc_kernel(const GruTcParams p) {
     for (int i = tid; i < n16; i += kTcThreads) reinterpret_cast<uint4*>(sW)[i] = __ldg(src + i);
     for (int i = tid; i < 384; i += kTcThreads)
       sBias[i] = p.bias[i] * (i < 2 * kHidden ? -kLog2e : 2.0f * kLog2e);
+    if (kLast)
+      for (int i = tid; i < kHidden * kTcMaxClasses; i += kTcThreads) sFc[i] = p.fcw[i];
   }
   tc::fence_proxy_async();            // weights written with generic stores, read by the MMA (async proxy)
   tc::fence_before_sync();
@@ -378,35 +380,34 @@ gru_tc_kernel(const GruTcParams p) {
       // r-gate MMAs run: 32 units per thread, partial sums of unit blocks 1..3 handed to block 0 through smem.
       auto fc_finish = [&](int t_done, bool emit) {
         const bool tl2 = p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && t_done < 32;
-        // class pairs (2c, 2c+1) are accumulated with packed FFMA2: h[j] broadcast x a weight pair from the constant bank
+        // class pairs (2c, 2c+1) are accumulated with packed FFMA2: h[j] broadcast x a weight pair; the [128][8] weights
+        // sit in shared memory and every lane reads the same row (broadcast, one wavefront per load)
         float2 part2[kTcMaxClasses / 2];
 #pragma unroll
         for (int c = 0; c < kTcMaxClasses / 2; ++c) part2[c] = make_float2(0.0f, 0.0f);
         if (emit) {                                                 // dynamic_rnn: zero output past the length
-          // one copy per unit block (and per pair count) so that every weight is a compile-time constant-bank address:
-          // the FMAs take uniform constant operands and the FC issues no shared/global load at all
-          auto fc_block = [&](auto UB, auto NP) {
-            constexpr int kU0 = kTcUnits * decltype(UB)::value;
-            constexpr int kPairs = decltype(NP)::value;
+          const float4* wrow = reinterpret_cast<const float4*>(sFc + u0 * kTcMaxClasses);
+          if (p.C <= 6) {                                           // the model's 6 classes: 3 pairs
 #pragma unroll
             for (int j = 0; j < kTcUnits; ++j) {
+              const float4 wa = wrow[2 * j];
+              const float2 wb = *reinterpret_cast<const float2*>(wrow + 2 * j + 1);
               const float2 hh = make_float2(h[j], h[j]);
+              part2[0] = __ffma2_rn(hh, make_float2(wa.x, wa.y), part2[0]);
+              part2[1] = __ffma2_rn(hh, make_float2(wa.z, wa.w), part2[1]);
+              part2[2] = __ffma2_rn(hh, wb, part2[2]);
+            }
+          } else {
 #pragma unroll
-              for (int c = 0; c < kPairs; ++c)
-                part2[c] = __ffma2_rn(hh, make_float2(p.fcw[(kU0 + j) * kTcMaxClasses + 2 * c],
-                                                      p.fcw[(kU0 + j) * kTcMaxClasses + 2 * c + 1]), part2[c]);
+            for (int j = 0; j < kTcUnits; ++j) {
+              const float4 wa = wrow[2 * j], wb = wrow[2 * j + 1];
+              const float2 hh = make_float2(h[j], h[j]);
+              part2[0] = __ffma2_rn(hh, make_float2(wa.x, wa.y), part2[0]);
+              part2[1] = __ffma2_rn(hh, make_float2(wa.z, wa.w), part2[1]);
+              part2[2] = __ffma2_rn(hh, make_float2(wb.x, wb.y), part2[2]);
+              part2[3] = __ffma2_rn(hh, make_float2(wb.z, wb.w), part2[3]);
             }
-          };
-          auto fc_pairs = [&](auto NP) {
-            switch (ublk) {
-              case 0: fc_block(std::integral_constant<int, 0>{}, NP); break;
-              case 1: fc_block(std::integral_constant<int, 1>{}, NP); break;
-              case 2: fc_block(std::integral_constant<int, 2>{}, NP); break;
-              default: fc_block(std::integral_constant<int, 3>{}, NP); break;
-            }
-          };
-          if (p.C <= 6) fc_pairs(std::integral_constant<int, 3>{});   // the model's 6 classes: 3 pairs
-          else fc_pairs(std::integral_constant<int, 4>{});
+          }
         }
         const float part[kTcMaxClasses] = {part2[0].x, part2[0].y, part2[1].x, part2[1].y,
                                            part2[2].x, part2[2].y, part2[3].x, part2[3].y};
@@ -590,7 +591,8 @@ gru_tc_kernel(const GruTcParams p) {
 
 
 static size_t gru_tc_smem_bytes(int ktot) {
-  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + 3 * kTcTile * 8) + kNumBars * sizeof(uint64_t) + 16;
+  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + 3 * kTcTile * 8 + kHidden * kTcMaxClasses) +
+         kNumBars * sizeof(uint64_t) + 16;
 }
 
 // Pack one layer's TF kernels into the fp16 canonical [384, kxw+128] B operand: [Wx_hi | Wx_lo (split) | Wh].

@@ -57,6 +57,7 @@ def parse_args():
                     "latency is one wave's, not the whole batch's")
     ap.add_argument("--depth", type=int, default=2, help="e2e: waves in flight")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local cores")
     ap.add_argument("--cpu-streams", type=int, default=0, help="CPU sample: streams (default 64 per host core)")
     ap.add_argument("--cpu-chunks", type=int, default=0, help="CPU sample: chunks per step (default: calibrated)")
     return ap.parse_args()
@@ -264,6 +265,7 @@ def run_ours(args, rank, world, local_rank):
 
     from keyword_spotting_b200 import Config, DeployModel, ModelWeights, StreamingDetector, _lib, _tensors, sharding
 
+    host_binding = sharding.bind_host_to_gpu(local_rank) if not args.no_bind else {"bound": False, "why": "--no-bind"}
     cfg = Config(n_mel=40)
     model = DeployModel(cfg, ModelWeights.random_init(cfg, seed=1234), device=device, precision=args.precision)
     S = args.streams
@@ -438,7 +440,7 @@ def run_ours(args, rank, world, local_rank):
                     full_batch_step_ms_p99=per_sorted[min(len(per_sorted) - 1, int(0.99 * len(per_sorted)))],
                     kernels_ms=dict(frontend=fe_ms / k_iters, gru_2_layers=gru_ms / k_iters, step_total=ms_per_step),
                     roofline=roofline, roofline_other=[roofline_other], cpu_baseline=cpu, e2e=e2e,
-                    gpu_launches=4 * args.steps, clocks=clocks,
+                    gpu_launches=4 * args.steps, clocks=clocks, host_binding=host_binding,
                     triggers=int(trig_total.item()))
         print(json.dumps(line), flush=True)
     det.close()

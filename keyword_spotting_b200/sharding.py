@@ -64,3 +64,33 @@ def reduce_sum_scalar(value: float, device=None, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return float(t.item())
+
+
+def bind_host_to_gpu(device_index: int) -> dict:
+    """Pin this process to the CPU cores (NUMA node) that are local to GPU `device_index`, BEFORE any pinned host
+    buffer is allocated: the host side of the streaming server is one process per GPU that feeds 55 GB/s of PCM
+    through page-locked staging buffers, and Linux places those pages on the node the allocating thread runs on.
+    With 8 ranks on a two-socket box an unbound rank lands on the far socket half of the time and its H2D copies
+    cross the socket interconnect.  Returns what was done (for the bench record); never raises.
+    """
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(device_index)       # honours CUDA_VISIBLE_DEVICES remapping
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(
+                ("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"bound": True, "cpus": len(allowed), "first_cpu": allowed[0], "last_cpu": allowed[-1]}
+    except Exception as e:                                     # no NVML / restricted container: run unbound
+        info["why"] = "%s: %s" % (type(e).__name__, e)
+    return info

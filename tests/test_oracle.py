@@ -186,6 +186,36 @@ def test_mel_basis_properties():
         assert (np.diff(peaks) > 0).all()
 
 
+def test_mel_basis_matches_an_independent_slaney_implementation():
+    """librosa is not installable here; `transformers.audio_utils.mel_filter_bank(norm='slaney', mel_scale='slaney')` is
+    an independent third-party implementation of the same `librosa.filters.mel` definition the reference calls
+    (models/rnn_ctc.py:139-144: sr=16000, n_fft=400, fmin=300, fmax=8000).  It pins row a6's constant."""
+    audio_utils = pytest.importorskip("transformers.audio_utils")
+    for M in (40, 60):
+        fb = audio_utils.mel_filter_bank(num_frequency_bins=201, num_mel_filters=M, min_frequency=300.0,
+                                         max_frequency=8000.0, sampling_rate=16000, norm="slaney", mel_scale="slaney")
+        np.testing.assert_allclose(om.slaney_mel_basis(n_mels=M), fb.T, rtol=0, atol=1e-15)
+        w = om.init_weights(seed=1, n_mel=M)
+        np.testing.assert_array_equal(w.mel_basis, fb.astype(np.float32))     # [201, M] f32 constant, as the graph holds it
+
+
+def test_framing_and_rfft_magnitude_match_numpy_stride_tricks():
+    """Row a4/a5 against an independent formulation: frames by stride tricks (utils/stft.py:67-79 builds the same
+    index grid), |rfft| by an explicit DFT matrix in float64."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 2000))
+    fr = np.lib.stride_tricks.sliding_window_view(x, 400, axis=1)[:, ::160]
+    np.testing.assert_array_equal(om.frame(x), fr)
+    n = np.arange(400)
+    dft = np.exp(-2j * np.pi * np.outer(n, np.arange(201)) / 400)
+    want = np.abs(fr @ dft)
+    got = np.abs(np.fft.rfft(om.frame(x), n=400, axis=-1))
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+    w = om.init_weights(seed=1, n_mel=40)
+    mel = om.pcm_to_mel(x, w, np.float64)
+    np.testing.assert_allclose(mel, want @ w.mel_basis.astype(np.float64), rtol=0, atol=1e-9)
+
+
 def test_num_frames_and_framing():
     assert om.num_frames(4800) == 28 and om.num_frames(5120) == 30 and om.num_frames(48000) == 298
     assert om.num_frames(400) == 1 and om.num_frames(399) == 0

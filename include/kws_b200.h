@@ -294,6 +294,11 @@ int kws_debug_tc_gemm(const float* A, const float* B_host, float* D, int N, int 
  * tensor-core GRU launch; see csrc/gru_tc.cu.  host_out may be NULL (only set the switch).               */
 int kws_debug_tc_timeline(int enable, long long* host_out, int count);
 
+/* Debug: per-part device time of kws_stream_step (front end incl. the fused VAD/tail pre-step | GRU layers | decode
+ * + trigger), CUDA events on the step's stream.  While enabled every step synchronises; ms_out3 receives the sums
+ * over *steps_out steps since it was enabled (either may be NULL).  Switching resets the sums.             */
+int kws_debug_step_timing(int enable, double* ms_out3, long long* steps_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,7 @@ _SIGNATURES = {
     "kws_attention_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "kws_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kws_debug_tc_timeline": (c_int, [c_int, c_void_p, c_int]),
+    "kws_debug_step_timing": (c_int, [c_int, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

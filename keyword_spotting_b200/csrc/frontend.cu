@@ -186,9 +186,12 @@ frontend_kernel(const FrontendParams p) {
       const float4 f = quad_to_float(pre[r]);
       if (r < kFeQuadRounds - 1 || last_quad_ok) *reinterpret_cast<float4*>(my_stage + (4 * kFeThreads + 4 * kFeSkew) * r) = f;
       const int q = q0 + 4 * tid + 4 * kFeThreads * r;
+      if (!p.fuse_pre) continue;
       if (!quad_split) {
+        // the carried tail is shorter than one round (<= 399 samples), so only round 0 of the first item can hold old samples
         const float a = (fabsf(f.x) + fabsf(f.y)) + (fabsf(f.z) + fabsf(f.w));
-        acc += q >= head_len ? a : 0.0f;
+        if (r == 0) acc += q >= head_len ? a : 0.0f;
+        else acc += a;
       } else {
         acc += (q >= head_len ? fabsf(f.x) : 0.0f) + (q + 1 >= head_len ? fabsf(f.y) : 0.0f) +
                (q + 2 >= head_len ? fabsf(f.z) : 0.0f) + (q + 3 >= head_len ? fabsf(f.w) : 0.0f);
@@ -236,8 +239,7 @@ frontend_kernel(const FrontendParams p) {
       }
     }
     if (p.fuse_pre) {                                 // block sum of |x| over the chunk (exact integers)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) vad_acc += __shfl_xor_sync(0xffffffffu, vad_acc, o);
+      vad_acc = __reduce_add_sync(0xffffffffu, vad_acc);
       if (lane == 0) red[warp] = vad_acc;
     }
     __syncthreads();
@@ -247,9 +249,21 @@ frontend_kernel(const FrontendParams p) {
       const int keep = total_len >= kFft ? (total_len - kFft) % kHop + (kFft - kHop) : total_len;
       const int start = total_len - keep;
       int16_t* tnext = p.tail_next + s * 400;
-      for (int i = tid; i < keep; i += kFeThreads) {
-        const int w = start + i;
-        tnext[i] = static_cast<int16_t>(win[w + kFeSkew * (w / kFeBlock)]);
+      if (p.vec_ok && ((head_len | total_len | start) & 3) == 0) {
+        // the kept samples are whole quads that some threads still hold as loaded: 8-byte stores straight from registers
+#pragma unroll
+        for (int r = 0; r < kFeQuadRounds; ++r) {
+          const int r0 = q0 + 4 * kFeThreads * r;                   // first sample of the round (block-uniform test)
+          if (r0 + 4 * kFeThreads > start && r0 < total_len) {
+            const int q = r0 + 4 * tid;
+            if (q >= start && q < total_len) *reinterpret_cast<uint2*>(tnext + (q - start)) = pre[r];
+          }
+        }
+      } else {
+        for (int i = tid; i < keep; i += kFeThreads) {
+          const int w = start + i;
+          tnext[i] = static_cast<int16_t>(win[w + kFeSkew * (w / kFeBlock)]);
+        }
       }
       if (tid == 0) {
         long long sum = 0;

@@ -305,6 +305,17 @@ gru_tc_kernel(const GruTcParams p) {
           h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
         }
       }
+      // layer 0: this thread's first 16-byte chunk of step 0, the chunk strides per step and per chunk, its valid chunks
+      const int x_k0 = (p.kx / 4) * ublk;
+      int nqv = (p.in_dim - x_k0 + 3) >> 2;
+      nqv = nqv < 0 ? 0 : (nqv > xq ? xq : nqv);
+      if (!p.x_tiled && !ok) nqv = 0;                              // row-major: rows past S do not exist
+      const bool x_vec = p.x_tiled || ((p.in_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x_f32) & 15) == 0);
+      const long x_q4 = p.in_dim >> 2;
+      const long x_step = p.x_tiled ? x_q4 * kTcTile : x_q4;
+      const int x_qs = p.x_tiled ? kTcTile : 1;
+      const float4* x_base = reinterpret_cast<const float4*>(p.x_f32) +
+                             (p.x_tiled ? (tile * p.n * x_q4 + (x_k0 >> 2)) * kTcTile + row : sr * p.n * x_q4 + (x_k0 >> 2));
       // x_t of this thread: K elements [ (kx/4)*ublk, +kx/4 ) of the row, as packed fp16 pairs (hi, and lo when split)
       // layer 0 keeps the raw fp32 values (xf) and splits them into fp16 hi/lo only when they are written to TMEM, so
       // the global loads issued under the u gate are not waited for until the candidate phase
@@ -320,27 +331,40 @@ gru_tc_kernel(const GruTcParams p) {
             xr[kFirst ? 0 : 4 * q] = v.x; xr[kFirst ? 0 : 4 * q + 1] = v.y;
             xr[kFirst ? 0 : 4 * q + 2] = v.z; xr[kFirst ? 0 : 4 * q + 3] = v.w;
           }
-        } else {
-          const int k0 = (p.kx / 4) * ublk;
+        } else if (x_vec) {
+          // 16-byte chunks: stream-tiled mel (chunk c of stream `row` at ((tile*n + t)*Q + c)*128 + row, Q = in_dim/4) or
+          // row-major rows whose chunks are consecutive.  Base address, strides and this thread's number of chunks are
+          // fixed per tile: per step one multiply and up to 8 predicated loads
+          const float4* src = x_base + static_cast<long>(t) * x_step;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            if (q < xq) {
-              const int k = k0 + 4 * q;
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (k < p.in_dim) {
-                if (p.x_tiled) {
-                  // float4 chunk c of stream `row` sits at ((tile*n + t)*Q + c)*128 + row, Q = in_dim/4
-                  v = __ldg(reinterpret_cast<const float4*>(p.x_f32) +
-                            ((tile * p.n + t) * static_cast<long>(p.in_dim / 4) + (k >> 2)) * kTcTile + row);
-                } else if (ok) {
-                  const float* src = p.x_f32 + (sr * p.n + t) * static_cast<long>(p.in_dim) + k;
-                  v.x = __ldg(src);
-                  if (k + 1 < p.in_dim) v.y = __ldg(src + 1);
-                  if (k + 2 < p.in_dim) v.z = __ldg(src + 2);
-                  if (k + 3 < p.in_dim) v.w = __ldg(src + 3);
-                }
-              }
-              xf[kFirst ? q : 0] = v;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < nqv) v = __ldg(src + q * x_qs);
+            xf[kFirst ? q : 0] = v;
+          }
+        } else {
+          // row-major [S, n, in_dim] with in_dim % 4 != 0 or an unaligned base: element-wise with bounds (rare, slow)
+          const float* src = p.x_f32 + (sr * p.n + t) * static_cast<long>(p.in_dim) + x_k0;
+#pragma unroll 1
+          for (int q = 0; q < 8; ++q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int k = x_k0 + 4 * q;
+            if (q < nqv) {
+              v.x = __ldg(src + 4 * q);
+              if (k + 1 < p.in_dim) v.y = __ldg(src + 4 * q + 1);
+              if (k + 2 < p.in_dim) v.z = __ldg(src + 4 * q + 2);
+              if (k + 3 < p.in_dim) v.w = __ldg(src + 4 * q + 3);
+            }
+            // (no dynamic register indexing: the loop is not unrolled)
+            if (q == 0) xf[0] = v;
+            if (kFirst) {
+              if (q == 1) xf[kFirst ? 1 : 0] = v;
+              if (q == 2) xf[kFirst ? 2 : 0] = v;
+              if (q == 3) xf[kFirst ? 3 : 0] = v;
+              if (q == 4) xf[kFirst ? 4 : 0] = v;
+              if (q == 5) xf[kFirst ? 5 : 0] = v;
+              if (q == 6) xf[kFirst ? 6 : 0] = v;
+              if (q == 7) xf[kFirst ? 7 : 0] = v;
             }
           }
         }
@@ -663,7 +687,7 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     p.C = m->cfg.num_classes;
     p.probs = a.probs;
     p.logits = a.logits;
-    p.timeline = g_tc_timeline_on;
+    p.timeline = (g_tc_timeline_on == 1 || g_tc_timeline_on == 2 + l) ? 1 : 0;      // 1: every layer (the last one stays), 2 + l: layer l only
     for (int j = 0; j < kHidden; ++j)
       for (int c = 0; c < kTcMaxClasses; ++c) p.fcw[j * kTcMaxClasses + c] = c < m->cfg.num_classes ? m->fc_w_host[j * m->cfg.num_classes + c] : 0.0f;
     for (int c = 0; c < kTcMaxClasses; ++c) p.fcb[c] = c < m->cfg.num_classes ? m->fc_b_host[c] : 0.0f;

@@ -323,6 +323,25 @@ extern "C" int kws_stream_copy_state(kws_stream* st, float* state_out, void* str
   return KWS_OK;
 }
 
+// Debug: device time of the three parts of a step (front end incl. the fused pre-step | GRU layers | decode + trigger),
+// measured with CUDA events on the step's stream.  Enabling it makes every step synchronise -- never on in production.
+static int g_step_timing_on = 0;
+static double g_step_ms[3] = {0.0, 0.0, 0.0};
+static long g_step_count = 0;
+extern "C" int kws_debug_step_timing(int enable, double* ms_out3, long long* steps_out) {
+  kws::clear_error();
+  if (ms_out3) {
+    for (int i = 0; i < 3; ++i) ms_out3[i] = g_step_ms[i];
+  }
+  if (steps_out) *steps_out = g_step_count;
+  if (enable != g_step_timing_on) {
+    g_step_timing_on = enable;
+    g_step_ms[0] = g_step_ms[1] = g_step_ms[2] = 0.0;
+    g_step_count = 0;
+  }
+  return KWS_OK;
+}
+
 extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk_len, int64_t ld_pcm,
                                int32_t* trigger_out, float* probs_out, int32_t* nframes_out, void* stream) {
   clear_error();
@@ -350,6 +369,11 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
   src.head_len = st->tail_len[cur];
   const bool fused = frontend_can_fuse_pre(chunk_len, kTailCap);
   const bool tiled = mel_can_tile(m);
+  cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (g_step_timing_on) {
+    for (int i = 0; i < 4; ++i) KWS_CUDA_OK(cudaEventCreate(&tev[i]));
+    KWS_CUDA_OK(cudaEventRecord(tev[0], cs));
+  }
   if (fused) {
     // one pass over the chunk: VAD + tail carry + frame count + framing/FFT/mel
     FrontendPre pre;
@@ -372,6 +396,7 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
       int rc = launch_frontend(m, src, S, n_step, st->nframes, st->mel, cs, nullptr, tiled);
       if (rc != KWS_OK) return rc;
     }
+    if (tev[1]) KWS_CUDA_OK(cudaEventRecord(tev[1], cs));
     int rc = KWS_OK;
     GruArgs a;
     a.x = st->mel;
@@ -393,11 +418,25 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
         st->state, S, m->cfg.num_layers, st->silence);
     KWS_LAUNCH_OK("zero_silent_state_kernel");
   }
+  if (tev[2]) KWS_CUDA_OK(cudaEventRecord(tev[2], cs));
   stream_post_kernel<<<static_cast<unsigned>(ceil_div(S, 128)), 128, 0, cs>>>(
       st->probs, n_step, C, S, st->cfg.window_chunks, st->fpad, st->cfg.decode_thres, st->kw, st->silence,
       st->nframes, st->tok, st->slot_frames, st->win_head, st->win_n, st->state, m->cfg.num_layers,
       st->trigger, trigger_out);
   KWS_LAUNCH_OK("stream_post_kernel");
+  if (tev[0]) {
+    KWS_CUDA_OK(cudaEventRecord(tev[3], cs));
+    KWS_CUDA_OK(cudaEventSynchronize(tev[3]));
+    if (n_step > 0) {
+      for (int i = 0; i < 3; ++i) {
+        float ms = 0.0f;
+        KWS_CUDA_OK(cudaEventElapsedTime(&ms, tev[i], tev[i + 1]));
+        g_step_ms[i] += ms;
+      }
+      ++g_step_count;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(tev[i]);
+  }
   st->cur = nxt;
   if (probs_out && n_step > 0) {
     KWS_CUDA_OK(cudaMemcpy2DAsync(probs_out, sizeof(float) * st->max_frames * C, st->probs,

@@ -51,6 +51,26 @@ for S, T in ((4096, 298), (131072, 450)):
     for name, mode in (("ctc_decode", prediction.MODE_CTC_DECODE), ("ctc_decode2", prediction.MODE_CTC_DECODE2)):
         ms = timeit(lambda: prediction.decode_batch(p, mode=mode, want_labels=False), iters=5)
         out["%s_%dx%d" % (name, S, T)] = dict(ms=ms, GBps=S * T * 6 * 4 / ms / 1e6)
+# ---- BASELINE configs[1]: offline batched inference, 4096 utterances x 3 s of int16 PCM already in HBM ->
+# front end -> 2L GRU-128 + FC + softmax (n = 298 frames) -> ctc_decode labels + trigger (main.py:263-314)
+from keyword_spotting_b200 import Config, DeployModel, ModelWeights
+from keyword_spotting_b200.rnn_ctc import INPUT_X, INITIAL_STATES, SOFTMAX, RNN_STATES
+cfg = Config(n_mel=40)
+dm = DeployModel(cfg, ModelWeights.random_init(cfg, seed=1234))
+for S in (4096, 32768):
+    pcm16 = (torch.randn((S, 48000), device="cuda", generator=g) * 800).clamp_(-32768, 32767).to(torch.int16)
+    st0 = torch.zeros((2, S, 128), device="cuda")
+
+    def offline():
+        probs, _ = dm.run([SOFTMAX, RNN_STATES], {INPUT_X: pcm16, INITIAL_STATES: st0})
+        return prediction.decode_batch(probs, mode=prediction.MODE_CTC_DECODE, want_labels=True)
+
+    ms = timeit(offline, iters=5)
+    ms_fe = timeit(lambda: dm.frontend(pcm16), iters=5)
+    out["offline_config2_S%d_3s" % S] = dict(ms=ms, ms_frontend=ms_fe, utterances_per_s=S / ms * 1e3, audio_s_per_s=3.0 * S / ms * 1e3,
+                                             gru_tiles=S // 128)
+    del pcm16, st0
+dm.close()
 # ---- attention_ctc forward, config 5: batched 8 s utterances (T = 798 mel frames of 60 bands -> T' = 400)
 from keyword_spotting_b200 import AttentionConfig, AttentionDeployModel
 am = AttentionDeployModel(AttentionConfig())

@@ -249,15 +249,14 @@ frontend_kernel(const FrontendParams p) {
       const int keep = total_len >= kFft ? (total_len - kFft) % kHop + (kFft - kHop) : total_len;
       const int start = total_len - keep;
       int16_t* tnext = p.tail_next + s * 400;
-      if (p.vec_ok && ((head_len | total_len | start) & 3) == 0) {
-        // the kept samples are whole quads that some threads still hold as loaded: 8-byte stores straight from registers
-#pragma unroll
-        for (int r = 0; r < kFeQuadRounds; ++r) {
-          const int r0 = q0 + 4 * kFeThreads * r;                   // first sample of the round (block-uniform test)
-          if (r0 + 4 * kFeThreads > start && r0 < total_len) {
-            const int q = r0 + 4 * tid;
-            if (q >= start && q < total_len) *reinterpret_cast<uint2*>(tnext + (q - start)) = pre[r];
-          }
+      if (((start | keep) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.tail_next) & 7) == 0) {
+        // whole quads: the first keep/4 (<= 100) threads convert four staged samples back (exact) and store 8 bytes
+        if (4 * tid < keep) {
+          const int w = start + 4 * tid;
+          const float4 f = *reinterpret_cast<const float4*>(win + w + kFeSkew * (w / kFeBlock));
+          const unsigned lo = (static_cast<unsigned>(__float2int_rn(f.x)) & 0xffffu) | (static_cast<unsigned>(__float2int_rn(f.y)) << 16);
+          const unsigned hi = (static_cast<unsigned>(__float2int_rn(f.z)) & 0xffffu) | (static_cast<unsigned>(__float2int_rn(f.w)) << 16);
+          *reinterpret_cast<uint2*>(tnext + 4 * tid) = make_uint2(lo, hi);
         }
       } else {
         for (int i = tid; i < keep; i += kFeThreads) {
@@ -265,13 +264,14 @@ frontend_kernel(const FrontendParams p) {
           tnext[i] = static_cast<int16_t>(win[w + kFeSkew * (w / kFeBlock)]);
         }
       }
-      if (tid == 0) {
-        long long sum = 0;
-#pragma unroll
-        for (int w = 0; w < kFeWarps; ++w) sum += red[w];
-        p.silence[s] = sum > p.vad_limit ? 0 : 1;
-        p.nframes_out[s] = nfr;
-        p.len_next[s] = keep;
+      if (warp == 0) {                                 // <= 10 partial sums of at most 20 * 32768 each: int is enough
+        const int part = lane < kFeWarps ? red[lane] : 0;
+        const int sum = __reduce_add_sync(0xffffffffu, part);
+        if (lane == 0) {
+          p.silence[s] = static_cast<long long>(sum) > p.vad_limit ? 0 : 1;
+          p.nframes_out[s] = nfr;
+          p.len_next[s] = keep;
+        }
       }
     }
 

@@ -146,7 +146,8 @@ frontend_kernel(const FrontendParams p) {
 #pragma unroll
       for (int r = 0; r < kFeQuadRounds; ++r) {
         const int q = q0 + 4 * tid + 4 * kFeThreads * r;
-        const int16_t* src = (q < head_len ? head : body) + q;
+        // the carried tail is shorter than one round (<= 399 samples): only round 0 can read it
+        const int16_t* src = (r == 0 && q < head_len ? head : body) + q;
         uint2 v = make_uint2(0u, 0u);
         if (q < total_len && (r < kFeQuadRounds - 1 || last_quad_ok)) v = __ldg(reinterpret_cast<const uint2*>(src));
         pre[r] = v;
@@ -179,24 +180,21 @@ frontend_kernel(const FrontendParams p) {
   // returns the thread's sum of |x| over the NEW samples (detector.py:168), exact in fp32 (<= 20 * 32768); samples
   // beyond the signal were loaded as zeros
   auto store_quads = [&](int q0, int head_len, const uint2 (&pre)[kFeQuadRounds]) {
-    float acc = 0.0f;
-    const bool quad_split = (head_len & 3) != 0;                      // a quad may straddle the tail/chunk boundary
+    float4 f[kFeQuadRounds];
 #pragma unroll
     for (int r = 0; r < kFeQuadRounds; ++r) {
-      const float4 f = quad_to_float(pre[r]);
-      if (r < kFeQuadRounds - 1 || last_quad_ok) *reinterpret_cast<float4*>(my_stage + (4 * kFeThreads + 4 * kFeSkew) * r) = f;
-      const int q = q0 + 4 * tid + 4 * kFeThreads * r;
-      if (!p.fuse_pre) continue;
-      if (!quad_split) {
-        // the carried tail is shorter than one round (<= 399 samples), so only round 0 of the first item can hold old samples
-        const float a = (fabsf(f.x) + fabsf(f.y)) + (fabsf(f.z) + fabsf(f.w));
-        if (r == 0) acc += q >= head_len ? a : 0.0f;
-        else acc += a;
-      } else {
-        acc += (q >= head_len ? fabsf(f.x) : 0.0f) + (q + 1 >= head_len ? fabsf(f.y) : 0.0f) +
-               (q + 2 >= head_len ? fabsf(f.z) : 0.0f) + (q + 3 >= head_len ? fabsf(f.w) : 0.0f);
-      }
+      f[r] = quad_to_float(pre[r]);
+      if (r < kFeQuadRounds - 1 || last_quad_ok) *reinterpret_cast<float4*>(my_stage + (4 * kFeThreads + 4 * kFeSkew) * r) = f[r];
     }
+    if (!p.fuse_pre) return 0;
+    // sum of |x| over the NEW samples.  The carried tail is shorter than one round (<= 399 samples), so only round 0
+    // of the first item can hold old samples; quads beyond the signal were loaded as zeros
+    float acc = 0.0f;
+#pragma unroll
+    for (int r = 1; r < kFeQuadRounds; ++r) acc += (fabsf(f[r].x) + fabsf(f[r].y)) + (fabsf(f[r].z) + fabsf(f[r].w));
+    const int q = q0 + 4 * tid;
+    acc += (q >= head_len ? fabsf(f[0].x) : 0.0f) + (q + 1 >= head_len ? fabsf(f[0].y) : 0.0f) +
+           (q + 2 >= head_len ? fabsf(f[0].z) : 0.0f) + (q + 3 >= head_len ? fabsf(f[0].w) : 0.0f);
     return static_cast<int>(acc);
   };
 

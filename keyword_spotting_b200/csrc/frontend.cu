@@ -69,6 +69,7 @@ struct FrontendParams {
   int vec_ok;               // int16 sources are 8-byte aligned with row strides % 4 == 0
   float* mel_out;           // [S, max_frames, n_mel], or stream-tiled (common.cuh) when tiled_out
   int tiled_out;
+  unsigned q_magic;         // ceil(2^32 / (n_mel / 4)): i / Q == umulhi(i, q_magic) for i < 2^16
   float mag_scale;          // 0.5 * (int16 input ? 2^-15 : 1), applied to the finished band sums
   // fused server pre-step (only with groups == 1 and int16 input): VAD, frame count, next tail
   int fuse_pre;
@@ -135,7 +136,7 @@ frontend_kernel(const FrontendParams p) {
   // Thread t owns the quads of stream samples q0 + 4t + 1280r (r < 5; the fifth round only for t < 60).
   const bool last_quad_ok = tid < kFeLastQuads;
   auto load_quads = [&](long item, int head_len, uint2 (&pre)[kFeQuadRounds]) {
-    const long s = item / p.groups;
+    const long s = p.groups == 1 ? item : item / p.groups;       // the server's chunks are one work item per stream
     const int q0 = static_cast<int>(item - s * p.groups) * kFeItemHop;
     const int total_len = head_len + p.src.body_len;
     // both pointers are indexed by the stream sample number
@@ -202,12 +203,12 @@ frontend_kernel(const FrontendParams p) {
   uint2 pre[kFeQuadRounds];
   int head_len = 0;
   if (i16 && item < items) {
-    head_len = p.src.head_len ? p.src.head_len[item / p.groups] : 0;
+    head_len = p.src.head_len ? p.src.head_len[p.groups == 1 ? item : item / p.groups] : 0;
     load_quads(item, head_len, pre);
   }
 
   for (; item < items; item += gridDim.x) {
-    const long s = item / p.groups;
+    const long s = p.groups == 1 ? item : item / p.groups;
     const int g = static_cast<int>(item - s * p.groups);
     if (!i16) head_len = p.src.head_len ? p.src.head_len[s] : 0;
     const int total_len = head_len + p.src.body_len;
@@ -219,7 +220,7 @@ frontend_kernel(const FrontendParams p) {
     // the next item's carried-tail length is needed for its addresses: fetch it a whole item ahead
     const long next = item + gridDim.x;
     int head_len_next = 0;
-    if (i16 && next < items && p.src.head_len) head_len_next = p.src.head_len[next / p.groups];
+    if (i16 && next < items && p.src.head_len) head_len_next = p.src.head_len[p.groups == 1 ? next : next / p.groups];
 
     // ---- stage the window: stream samples [q0, q0 + 5360) -> win[i + 20*(i/320)], zero beyond the signal.
     int vad_acc = 0;
@@ -354,7 +355,8 @@ frontend_kernel(const FrontendParams p) {
           dst4 += (s * p.max_frames + f0) * static_cast<long>(Q);
         }
         for (int i = tid; i < (total >> 2); i += kFeThreads) {
-          const int f = i / Q, c = i - f * Q;
+          const int f = Q == 1 ? i : static_cast<int>(__umulhi(static_cast<unsigned>(i), p.q_magic));   // i / Q, i < 2^16
+          const int c = i - f * Q;
           const float* src = out_tile + f * Mp + 4 * c;
           dst4[i * step] = make_float4(src[0], src[1], src[2], src[3]);
         }
@@ -447,6 +449,7 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
               reinterpret_cast<uintptr_t>(src.head) % 8 == 0 && src.ld_head % 4 == 0) ? 1 : 0;
   p.mel_out = mel_out;
   p.tiled_out = tiled_out ? 1 : 0;
+  p.q_magic = m->cfg.n_mel >= 4 ? static_cast<unsigned>(((1ull << 32) + (m->cfg.n_mel / 4) - 1) / (m->cfg.n_mel / 4)) : 0u;
   if (tiled_out && (m->cfg.n_mel & 3)) return fail(KWS_ERR_INVALID_ARGUMENT, "tiled mel output needs n_mel % 4 == 0");
   p.mag_scale = src.body_dtype == KWS_PCM_I16 ? 0.5f / 32768.0f : 0.5f;
   p.fuse_pre = 0;

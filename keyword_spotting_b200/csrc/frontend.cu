@@ -95,9 +95,10 @@ __device__ __forceinline__ int mag_index(int bin, int slot) { return (bin >> 1) 
 
 // four int16 samples of one 8-byte load -> floats (exact)
 __device__ __forceinline__ float4 quad_to_float(uint2 q) {
-  return make_float4(static_cast<float>(static_cast<short>(q.x & 0xffffu)), static_cast<float>(static_cast<int>(q.x) >> 16),
-                     static_cast<float>(static_cast<short>(q.y & 0xffffu)), static_cast<float>(static_cast<int>(q.y) >> 16));
+  return make_float4(static_cast<float>(static_cast<short>(q.x & 0xffffu)), static_cast<float>(static_cast<short>(q.x >> 16)),
+                     static_cast<float>(static_cast<short>(q.y & 0xffffu)), static_cast<float>(static_cast<short>(q.y >> 16)));
 }
+
 template <bool kQuadsInSmem>
 __global__ void __launch_bounds__(kFeThreads, 2)
 frontend_kernel(const FrontendParams p) {
@@ -123,6 +124,13 @@ frontend_kernel(const FrontendParams p) {
   const cpx* my_tw = twp + fft::tw_base(warp, lane);
   float* out_tile = reinterpret_cast<float*>(buf);
   const long items = p.S * p.groups;
+  // stream of a work item: no division for the server's one-item chunks, a 32-bit one whenever the item count allows
+  const bool items32 = items < (1L << 32);
+  auto stream_of = [&](long item) -> long {
+    if (p.groups == 1) return item;
+    if (items32) return static_cast<long>(static_cast<unsigned>(item) / static_cast<unsigned>(p.groups));
+    return item / p.groups;
+  };
   const bool i16 = p.src.body_dtype == KWS_PCM_I16;
   const int M = p.n_mel;
   const int Mp = M | 1;                               // odd row stride of the [32][M] output tile: conflict-free band writes
@@ -136,7 +144,7 @@ frontend_kernel(const FrontendParams p) {
   // Thread t owns the quads of stream samples q0 + 4t + 1280r (r < 5; the fifth round only for t < 60).
   const bool last_quad_ok = tid < kFeLastQuads;
   auto load_quads = [&](long item, int head_len, uint2 (&pre)[kFeQuadRounds]) {
-    const long s = p.groups == 1 ? item : item / p.groups;       // the server's chunks are one work item per stream
+    const long s = stream_of(item);
     const int q0 = static_cast<int>(item - s * p.groups) * kFeItemHop;
     const int total_len = head_len + p.src.body_len;
     // both pointers are indexed by the stream sample number
@@ -203,12 +211,12 @@ frontend_kernel(const FrontendParams p) {
   uint2 pre[kFeQuadRounds];
   int head_len = 0;
   if (i16 && item < items) {
-    head_len = p.src.head_len ? p.src.head_len[p.groups == 1 ? item : item / p.groups] : 0;
+    head_len = p.src.head_len ? p.src.head_len[stream_of(item)] : 0;
     load_quads(item, head_len, pre);
   }
 
   for (; item < items; item += gridDim.x) {
-    const long s = p.groups == 1 ? item : item / p.groups;
+    const long s = stream_of(item);
     const int g = static_cast<int>(item - s * p.groups);
     if (!i16) head_len = p.src.head_len ? p.src.head_len[s] : 0;
     const int total_len = head_len + p.src.body_len;
@@ -220,7 +228,7 @@ frontend_kernel(const FrontendParams p) {
     // the next item's carried-tail length is needed for its addresses: fetch it a whole item ahead
     const long next = item + gridDim.x;
     int head_len_next = 0;
-    if (i16 && next < items && p.src.head_len) head_len_next = p.src.head_len[p.groups == 1 ? next : next / p.groups];
+    if (i16 && next < items && p.src.head_len) head_len_next = p.src.head_len[stream_of(next)];
 
     // ---- stage the window: stream samples [q0, q0 + 5360) -> win[i + 20*(i/320)], zero beyond the signal.
     int vad_acc = 0;

@@ -183,7 +183,8 @@ gru_tc_kernel(const GruTcParams p) {
   float* sBias = reinterpret_cast<float*>(smem + static_cast<size_t>(384) * ktot * 2);   // [384] pre-scaled
   float* sXch = sBias + 384;                                               // [3][128][8] FC partials of unit blocks 1..3
   float* sFc = sXch + 3 * kTcTile * kTcMaxClasses;                         // [128][8] FC weights (last layer)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sFc + kHidden * kTcMaxClasses);     // [kNumBars]
+  float* sProb = sFc + kHidden * kTcMaxClasses;                            // [4 steps][6][128] parked probabilities (last layer)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sProb + (kLast ? 4 * 6 * kTcTile : 0));   // [kNumBars]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -286,6 +287,8 @@ gru_tc_kernel(const GruTcParams p) {
     const float* bR = sBias + u0;
     const float* bU = sBias + kHidden + u0;
     const float* bC = sBias + 2 * kHidden + u0;
+    // last layer, the model's 6 classes, 16-byte aligned rows: probabilities leave four steps at a time (fc_finish)
+    const bool probs_batched = kLast && p.C == 6 && (p.n & 1) == 0 && (reinterpret_cast<uintptr_t>(p.probs) & 15) == 0;
     uint32_t it = 0;
 
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -447,10 +450,21 @@ gru_tc_kernel(const GruTcParams p) {
           if (ok) {
             float lg[8];
             float mx = -INFINITY;
+            {
+              // the three other unit blocks' partial sums: 16-byte reads (a row is 32 bytes: conflict-free)
+              float o[3][8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              lg[c] = part[c] + sXch[row * 8 + c] + sXch[(kTcTile + row) * 8 + c] + sXch[(2 * kTcTile + row) * 8 + c] + p.fcb[c];
-              if (c < p.C) mx = fmaxf(mx, lg[c]);
+              for (int b = 0; b < 3; ++b) {
+                const float4 lo4 = *reinterpret_cast<const float4*>(sXch + (b * kTcTile + row) * 8);
+                const float4 hi4 = *reinterpret_cast<const float4*>(sXch + (b * kTcTile + row) * 8 + 4);
+                o[b][0] = lo4.x; o[b][1] = lo4.y; o[b][2] = lo4.z; o[b][3] = lo4.w;
+                o[b][4] = hi4.x; o[b][5] = hi4.y; o[b][6] = hi4.z; o[b][7] = hi4.w;
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                lg[c] = part[c] + o[0][c] + o[1][c] + o[2][c] + p.fcb[c];
+                if (c < p.C) mx = fmaxf(mx, lg[c]);
+              }
             }
             float e[8], sum = 0.0f;
 #pragma unroll
@@ -459,10 +473,33 @@ gru_tc_kernel(const GruTcParams p) {
               sum += e[c];
             }
             const float inv = rcp_approx(sum);                              // sum in [1, C]
-            float* pr = p.probs + (s * p.n + t_done) * p.C;
+            if (probs_batched) {
+              // Probabilities of four consecutive steps are parked in shared memory (a column per stream, touched by
+              // this thread only) and leave as 96 contiguous bytes per stream: 3 full sectors instead of 4 x 24
+              // scattered bytes.
+              const int kq = t_done & 3;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (c < p.C) pr[c] = e[c] * inv;
+              for (int c = 0; c < 6; ++c) sProb[(kq * 6 + c) * kTcTile + row] = e[c] * inv;
+              if (kq == 3 || t_done == p.n - 1) {
+                float4* dst = reinterpret_cast<float4*>(p.probs + (s * p.n + (t_done - kq)) * 6);
+                const int nq4 = ((kq + 1) * 6) >> 2;                 // whole float4s: 6 (4 steps), 4, 3, 1
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+                  if (i < nq4)
+                    dst[i] = make_float4(sProb[(4 * i) * kTcTile + row], sProb[(4 * i + 1) * kTcTile + row],
+                                         sProb[(4 * i + 2) * kTcTile + row], sProb[(4 * i + 3) * kTcTile + row]);
+                float* tail = reinterpret_cast<float*>(dst) + 4 * nq4;   // (kq+1)*6 mod 4 = 2 left over when kq is 0 or 2
+                if (((kq + 1) * 6) & 3) {
+                  tail[0] = sProb[(4 * nq4) * kTcTile + row];
+                  tail[1] = sProb[(4 * nq4 + 1) * kTcTile + row];
+                }
+              }
+            } else {
+              float* pr = p.probs + (s * p.n + t_done) * p.C;
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                if (c < p.C) pr[c] = e[c] * inv;
+            }
             if (p.logits) {
               float* lo = p.logits + (s * p.n + t_done) * p.C;
 #pragma unroll
@@ -614,9 +651,9 @@ gru_tc_kernel(const GruTcParams p) {
 }
 
 
-static size_t gru_tc_smem_bytes(int ktot) {
+static size_t gru_tc_smem_bytes(int ktot, bool last) {
   return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + 3 * kTcTile * 8 + kHidden * kTcMaxClasses) +
-         kNumBars * sizeof(uint64_t) + 16;
+         (last ? sizeof(float) * 4 * 6 * kTcTile : 0) + kNumBars * sizeof(uint64_t) + 16;
 }
 
 // Pack one layer's TF kernels into the fp16 canonical [384, kxw+128] B operand: [Wx_hi | Wx_lo (split) | Wh].
@@ -691,7 +728,7 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     for (int j = 0; j < kHidden; ++j)
       for (int c = 0; c < kTcMaxClasses; ++c) p.fcw[j * kTcMaxClasses + c] = c < m->cfg.num_classes ? m->fc_w_host[j * m->cfg.num_classes + c] : 0.0f;
     for (int c = 0; c < kTcMaxClasses; ++c) p.fcb[c] = c < m->cfg.num_classes ? m->fc_b_host[c] : 0.0f;
-    const size_t smem = gru_tc_smem_bytes(p.kxw + kHidden);
+    const size_t smem = gru_tc_smem_bytes(p.kxw + kHidden, last);
     const long blocks = ntiles < sm_count() ? ntiles : sm_count();
     const bool first = l == 0;
     auto launch = [&](auto kernel) -> int {

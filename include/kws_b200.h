@@ -294,6 +294,11 @@ int kws_debug_tc_gemm(const float* A, const float* B_host, float* D, int N, int 
  * tensor-core GRU launch; see csrc/gru_tc.cu.  host_out may be NULL (only set the switch).               */
 int kws_debug_tc_timeline(int enable, long long* host_out, int count);
 
+/* Debug / test (host only, needs no device): the front end's per-warp mel "quad" lists for a basis [201, n_mel]
+ * (csrc/frontend.cu, build_mel_quads).  quads_out receives records of 8 ints {4 weights (float bits), magnitude row byte
+ * offset, output band byte offset or -1, 0, 0}, 10 warps x the returned quads-per-warp; quads_out may be NULL.     */
+int kws_debug_mel_quads(const float* basis, int n_mel, int* quads_out, int capacity);
+
 /* Debug: per-part device time of kws_stream_step (front end incl. the fused VAD/tail pre-step | GRU layers | decode
  * + trigger), CUDA events on the step's stream.  While enabled every step synchronises; ms_out3 receives the sums
  * over *steps_out steps since it was enabled (either may be NULL).  Switching resets the sums.             */

@@ -106,6 +106,7 @@ _SIGNATURES = {
     "kws_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kws_debug_tc_timeline": (c_int, [c_int, c_void_p, c_int]),
     "kws_debug_step_timing": (c_int, [c_int, c_void_p, c_void_p]),
+    "kws_debug_mel_quads": (c_int, [c_void_p, c_int, c_void_p, c_int]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

@@ -24,6 +24,7 @@
 // conflict-free magnitude reads; the [32, M] result tile leaves as one contiguous block.  Persistent grid:
 // (resident CTAs per SM) x 148 SMs, grid-stride over work items.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -497,3 +498,23 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
 }
 
 }  // namespace kws
+
+// Debug / test hook (host only, no device needed): the per-warp mel quad lists of a basis [201, M].
+// quads_out receives up to `capacity` records of 8 ints {w0,w1,w2,w3 (float bits), magnitude byte offset, band byte
+// offset or -1, 0, 0} in warp-major order; returns quads per warp (all 10 warps carry the same number), or a
+// negative error code.
+extern "C" int kws_debug_mel_quads(const float* basis, int n_mel, int* quads_out, int capacity) {
+  kws::clear_error();
+  if (!basis || n_mel < 1 || n_mel > kws::kMaxMel) return kws::fail(KWS_ERR_INVALID_ARGUMENT, "bad basis / n_mel");
+  std::vector<kws::MelQuad> quads;
+  int qpw = 0;
+  kws::build_mel_quads(basis, n_mel, &quads, &qpw);
+  static_assert(sizeof(kws::MelQuad) == 32, "record layout");
+  const int n = static_cast<int>(quads.size());
+  if (quads_out) {
+    if (capacity < n) return kws::fail(KWS_ERR_INVALID_ARGUMENT, "capacity %d < %d quads", capacity, n);
+    memcpy(quads_out, quads.data(), sizeof(kws::MelQuad) * n);
+  }
+  return qpw;
+}
+

@@ -140,6 +140,48 @@ def test_mel_filterbank_equals_oracle_restatement():
         np.testing.assert_array_equal(mel_filterbank(n_mels=M), slaney_mel_basis(n_mels=M))
 
 
+def test_mel_quad_lists_cover_the_basis_exactly():
+    """The front end walks per-warp lists of 4-bin 'quads' instead of the dense [201, M] basis (csrc/frontend.cu,
+    build_mel_quads; host code, no device needed).  Summing the quads back must reproduce every weight bit for bit,
+    every band must be finished exactly once, quads start at even bins, and the 10 warps carry equal lengths."""
+    import ctypes
+    from keyword_spotting_b200 import _lib
+    from oracle.model import slaney_mel_basis
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    bases = [slaney_mel_basis(n_mels=40).T, slaney_mel_basis(n_mels=60).T]
+    dense = rng.standard_normal((201, 12)) * (rng.random((201, 12)) < 0.3)        # arbitrary sparse-ish basis
+    dense[:, 5] = 0.0                                                              # an empty band still writes its 0
+    bases.append(dense)
+    for basis in bases:
+        basis = np.ascontiguousarray(basis, np.float32)
+        M = basis.shape[1]
+        qpw = lib.kws_debug_mel_quads(basis.ctypes.data, M, None, 0)
+        assert qpw >= 1 and qpw % 2 == 0
+        rec = np.zeros((10 * qpw, 8), np.int32)
+        assert lib.kws_debug_mel_quads(basis.ctypes.data, M, rec.ctypes.data, rec.shape[0]) == qpw
+        w = rec[:, :4].copy().view(np.float32)
+        rebuilt = np.zeros((204, M), np.float32)
+        finished = np.zeros(M, int)
+        for warp in range(10):
+            band_rows = []
+            for q in range(qpw):
+                r = rec[warp * qpw + q]
+                assert r[4] % (66 * 4) == 0                     # byte offset of a bin-pair row of 66 floats
+                k0 = 2 * (r[4] // (66 * 4))
+                band_rows.append((k0, w[warp * qpw + q]))
+                if r[5] >= 0:
+                    b = r[5] // 4
+                    for k, wv in band_rows:
+                        rebuilt[k:k + 4, b] += wv
+                    finished[b] += 1
+                    band_rows = []
+            assert all((wv == 0).all() for _, wv in band_rows)  # trailing padding quads carry no weight
+        np.testing.assert_array_equal(finished, 1)
+        np.testing.assert_array_equal(rebuilt[:201], basis)
+        assert (rebuilt[201:] == 0).all()
+
+
 def test_weights_random_init_matches_oracle_recipe():
     from keyword_spotting_b200 import Config, ModelWeights
     from oracle import model as om

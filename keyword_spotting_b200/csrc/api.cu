@@ -72,6 +72,8 @@ static void free_model(kws_model* m) {
   }
   cudaFree(m->fc_w);
   cudaFree(m->fc_b);
+  for (cudaEvent_t e : m->aux_events) cudaEventDestroy(e);
+  if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
   cudaFree(m->scratch_mel);
   cudaFree(m->scratch_seq);
   delete m;

@@ -93,6 +93,8 @@ struct kws_model {
   int32_t cap_frames = 0;
   float* scratch_mel = nullptr;   // [S, n, M]
   float* scratch_seq = nullptr;   // layer hand-off [tiles, n, H, 64]
+  cudaStream_t aux_stream = nullptr;          // second stream + events of the layer pipeline for small batches (gru_tc.cu)
+  std::vector<cudaEvent_t> aux_events;
 };
 
 namespace kws {

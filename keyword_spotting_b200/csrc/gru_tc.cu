@@ -57,7 +57,8 @@ struct GruTcParams {
   int kxw;                     // x columns of the packed weights: 2*kx when the x product is split (layer 0), else kx
   int in_dim;                  // true x width
   long S;
-  int n;
+  int n;                       // frames of the whole sequence: the time stride of x, the hand-off, probs and logits
+  int t0, nt;                  // this launch runs frames [t0, t0 + nt) (the layers of long sequences are pipelined in time chunks)
   const float* x_f32;          // layer 0: mel fp32, [S, n, in_dim] row-major or stream-tiled (x_tiled, see common.cuh)
   int x_tiled;
   const __half* x_f16;         // layer > 0: fp16, stream-tiled [tile][t][16 chunks][128 streams][8 units]
@@ -257,7 +258,7 @@ gru_tc_kernel(const GruTcParams p) {
       };
       uint32_t it = 0;
       for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int t = 0; t < p.n; ++t, ++it) {
+        for (int t = 0; t < p.nt; ++t, ++it) {
           const uint32_t par = it & 1;
           mbar_acquire(&bars[kBarAX], par);
           issue_x(colDr, 0);                                                 // r gate, x-part (D_r is free since the last r epilogue)
@@ -288,15 +289,16 @@ gru_tc_kernel(const GruTcParams p) {
     const float* bU = sBias + kHidden + u0;
     const float* bC = sBias + 2 * kHidden + u0;
     // last layer, the model's 6 classes, 16-byte aligned rows: probabilities leave four steps at a time (fc_finish)
-    const bool probs_batched = kLast && p.C == 6 && (p.n & 1) == 0 && (reinterpret_cast<uintptr_t>(p.probs) & 15) == 0;
+    const bool probs_batched = kLast && p.C == 6 && ((p.n | p.t0) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.probs) & 15) == 0;
     uint32_t it = 0;
 
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long s = tile * kTcTile + row;
       const bool ok = s < p.S;
       const long sr = ok ? s : 0;
+      const int t_end = p.t0 + p.nt;
       const int len = ok ? (p.seq_len ? p.seq_len[s] : p.n) : 0;
-      const bool all_live = __all_sync(0xffffffffu, len >= p.n);     // warp-uniform: no select in the update
+      const bool all_live = __all_sync(0xffffffffu, len >= t_end);   // warp-uniform: no select in the update
       float h[kTcUnits];
       {
         const bool zero = !ok || (p.zero_state && p.zero_state[s]);
@@ -477,10 +479,10 @@ gru_tc_kernel(const GruTcParams p) {
               // Probabilities of four consecutive steps are parked in shared memory (a column per stream, touched by
               // this thread only) and leave as 96 contiguous bytes per stream: 3 full sectors instead of 4 x 24
               // scattered bytes.
-              const int kq = t_done & 3;
+              const int kq = (t_done - p.t0) & 3;
 #pragma unroll
               for (int c = 0; c < 6; ++c) sProb[(kq * 6 + c) * kTcTile + row] = e[c] * inv;
-              if (kq == 3 || t_done == p.n - 1) {
+              if (kq == 3 || t_done == t_end - 1) {
                 float4* dst = reinterpret_cast<float4*>(p.probs + (s * p.n + (t_done - kq)) * 6);
                 const int nq4 = ((kq + 1) * 6) >> 2;                 // whole float4s: 6 (4 steps), 4, 3, 1
 #pragma unroll
@@ -513,7 +515,7 @@ gru_tc_kernel(const GruTcParams p) {
 
       // ---- prologue: A_x <- x_0, A_h <- fp16(h).  All MMAs of the previous tile have completed (its last
       // commit was waited for by every thread), so both operand regions are free.
-      load_x(0);
+      load_x(p.t0);
       store_x();
       store_h();
       tc::wait_st();
@@ -521,9 +523,9 @@ gru_tc_kernel(const GruTcParams p) {
       mbar_arrive(&bars[kBarAX]);
       mbar_arrive(&bars[kBarAH]);
 
-      for (int t = 0; t < p.n; ++t, ++it) {
+      for (int t = p.t0; t < t_end; ++t, ++it) {
         const uint32_t par = it & 1;
-        const bool more = t + 1 < p.n;
+        const bool more = t + 1 < t_end;
         const bool tl = p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && t < 64;
         // ---- r gate: keep fp16(r*h) in registers until the u-gate MMAs have finished reading A_h
         uint32_t rh[kTcUnits / 2];
@@ -701,7 +703,8 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
   const long ntiles = ceil_div(a.S, kTcTile);
   const size_t per_buf = static_cast<size_t>(ntiles) * kTcTile * a.n * kHidden;     // halves (whole tiles)
   __half* seq = reinterpret_cast<__half*>(a.seq_scratch ? a.seq_scratch : m->scratch_seq);
-  for (int l = 0; l < L; ++l) {
+  // frames [t0, t0 + nt) of layer l on stream `cs`; `head` = the first chunk of the sequence (incoming state, VAD reset)
+  auto launch_layer = [&](int l, int t0, int nt, bool head, cudaStream_t cs) -> int {
     const bool last = l == L - 1;
     GruTcParams p;
     p.kx = m->layer[l].tc_kx;
@@ -709,16 +712,18 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     p.in_dim = m->layer[l].in_dim;
     p.S = a.S;
     p.n = a.n;
+    p.t0 = t0;
+    p.nt = nt;
     p.x_f32 = l == 0 ? a.x : nullptr;
     p.x_tiled = l == 0 && a.x_tiled ? 1 : 0;
     p.x_f16 = l == 0 ? nullptr : seq + ((l - 1) & 1) * per_buf;
     p.y_f16 = last ? nullptr : seq + (l & 1) * per_buf;
     p.wpack = static_cast<const __half*>(m->layer[l].tc_wpack);
     p.bias = m->layer[l].tc_bias;
-    p.h_in = a.state_in + static_cast<long>(l) * a.S * kHidden;
     p.h_out = a.state_out + static_cast<long>(l) * a.S * kHidden;
+    p.h_in = head ? a.state_in + static_cast<long>(l) * a.S * kHidden : p.h_out;
     p.seq_len = a.seq_len;
-    p.zero_state = a.zero_state;
+    p.zero_state = head ? a.zero_state : nullptr;
     p.fc_w = m->fc_w;
     p.fc_b = m->fc_b;
     p.C = m->cfg.num_classes;
@@ -733,7 +738,7 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     const bool first = l == 0;
     auto launch = [&](auto kernel) -> int {
       KWS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      kernel<<<static_cast<unsigned>(blocks), kTcThreads, smem, st>>>(p);
+      kernel<<<static_cast<unsigned>(blocks), kTcThreads, smem, cs>>>(p);
       return KWS_OK;
     };
     int rc;
@@ -741,7 +746,40 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     else rc = first ? launch(gru_tc_kernel<false, true>) : launch(gru_tc_kernel<false, false>);
     if (rc != KWS_OK) return rc;
     KWS_LAUNCH_OK("gru_tc_kernel");
+    return KWS_OK;
+  };
+
+  // Small batches of long sequences (BASELINE config 2: 4096 utterances x 298 frames = 32 tiles on 148 SMs): the two
+  // layers are pipelined in time chunks on two streams -- layer 1 runs chunk c while layer 0 runs chunk c + 1 -- so
+  // twice as many SMs work.  The recurrence itself is sequential; large batches fill the GPU without this.
+  constexpr int kChunk = 64;                                   // multiple of 4: the batched probability stores stay aligned
+  const bool pipelined = L == 2 && 2 * ntiles <= sm_count() && a.n >= 2 * kChunk && !g_tc_timeline_on;
+  if (!pipelined) {
+    for (int l = 0; l < L; ++l) {
+      const int rc = launch_layer(l, 0, a.n, true, st);
+      if (rc != KWS_OK) return rc;
+    }
+    return KWS_OK;
   }
+  if (!m->aux_stream) KWS_CUDA_OK(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+  const int nchunks = a.n / kChunk;                            // the last chunk takes the remainder
+  while (static_cast<int>(m->aux_events.size()) < nchunks + 1) {
+    cudaEvent_t e;
+    KWS_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    m->aux_events.push_back(e);
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    const int t0 = c * kChunk;
+    const int nt = c == nchunks - 1 ? a.n - t0 : kChunk;
+    int rc = launch_layer(0, t0, nt, c == 0, st);
+    if (rc != KWS_OK) return rc;
+    KWS_CUDA_OK(cudaEventRecord(m->aux_events[c], st));
+    KWS_CUDA_OK(cudaStreamWaitEvent(m->aux_stream, m->aux_events[c], 0));
+    rc = launch_layer(1, t0, nt, c == 0, m->aux_stream);
+    if (rc != KWS_OK) return rc;
+  }
+  KWS_CUDA_OK(cudaEventRecord(m->aux_events[nchunks], m->aux_stream));
+  KWS_CUDA_OK(cudaStreamWaitEvent(st, m->aux_events[nchunks], 0));
   return KWS_OK;
 }
 

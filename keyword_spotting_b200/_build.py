@@ -15,11 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libkws_b200.so")
 SOURCES = ["api.cu", "posenc.cu", "octbit.cu", "octbit_tc.cu", "frontend.cu", "gru.cu", "gru_tc.cu", "decode.cu", "stream.cu", "tc_debug.cu", "attention.cu"]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only
-    "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-]
+OBJ_DIR = os.path.join(HERE, "build")
+_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]   # B200 only
+NVCC_COMPILE_FLAGS = _ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+NVCC_LINK_FLAGS = _ARCH + ["-shared", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -50,17 +49,39 @@ def build(force: bool = False, verbose: bool = False) -> str:
             return LIB_PATH          # stale but usable (e.g. mtimes scrambled by a copy)
         raise ImportError("libkws_b200.so is not built and nvcc was not found; "
                           "keyword_spotting_b200 has no CPU fallback")
+    # one nvcc -c per source, in parallel (objects cached under csrc/../build/ by mtime), then one link step
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [f for f in _inputs() if not f.endswith(".cu")]
+    newest_header = max(os.path.getmtime(f) for f in headers if os.path.exists(f))
+    log = []
+
+    def compile_one(src):
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(path)
+                and os.path.getmtime(obj) > newest_header):
+            return obj, 0, ""
+        cmd = [nvcc] + NVCC_COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj + ".tmp"]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if proc.returncode == 0:
+            os.replace(obj + ".tmp", obj)
+        return obj, proc.returncode, proc.stdout
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for obj, rc, out in results:
+        log.append(out)
+        if rc != 0:
+            raise ImportError("nvcc failed building %s:\n%s" % (obj, out))
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-        print(" ".join(cmd))
+    cmd = [nvcc] + NVCC_LINK_FLAGS + ["-o", tmp] + [r[0] for r in results]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         if os.path.exists(tmp):
             os.remove(tmp)
-        raise ImportError("nvcc failed building libkws_b200.so:\n" + proc.stdout)
+        raise ImportError("nvcc failed linking libkws_b200.so:\n" + proc.stdout)
     if verbose:
-        print(proc.stdout)
+        print("".join(log))
     os.replace(tmp, LIB_PATH)
     return LIB_PATH

@@ -188,7 +188,7 @@ extern "C" int kws_model_get_precision(const kws_model* m) { return m ? m->preci
 
 namespace kws {
 int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st) {
-  return m->precision == KWS_PRECISION_FP32 ? launch_gru_fp32(m, a, st) : launch_gru_tc(m, a, st);
+  return model_uses_tc(m) ? launch_gru_tc(m, a, st) : launch_gru_fp32(m, a, st);
 }
 }  // namespace kws
 

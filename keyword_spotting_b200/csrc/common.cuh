@@ -126,7 +126,13 @@ void build_mel_quads(const float* basis /*[201, M] host*/, int M, std::vector<Me
 // Stream-tiled mel scratch (front end -> tensor-core GRU): float4 chunk c (of Q = M/4) of frame t of stream s sits at
 // float4 index ((s/128 * n + t) * Q + c) * 128 + s % 128, so the 128 threads of a GRU tile read, and the front end
 // writes, 16-byte pieces that are contiguous across streams.  Size: ceil(S/128)*128 * n * M floats.
-inline bool mel_can_tile(const kws_model* m) { return m->precision == KWS_PRECISION_TC_FP16 && m->cfg.n_mel % 4 == 0; }
+constexpr int kTcMaxClasses = 8;   // FC columns the tensor-core recurrent kernel keeps per thread (gru_tc.cu)
+// The tensor-core recurrent kernel serves models of up to kTcMaxClasses classes; wider FC layers run on the exact fp32
+// kernel whatever the requested precision (never a silently truncated softmax).
+inline bool model_uses_tc(const kws_model* m) {
+  return m->precision == KWS_PRECISION_TC_FP16 && m->cfg.num_classes <= kTcMaxClasses;
+}
+inline bool mel_can_tile(const kws_model* m) { return model_uses_tc(m) && m->cfg.n_mel % 4 == 0; }
 inline size_t mel_scratch_elems(int64_t S, int32_t n, int n_mel) {
   return static_cast<size_t>(ceil_div(S, 128) * 128) * static_cast<size_t>(n > 0 ? n : 1) * n_mel;
 }

@@ -480,11 +480,8 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
   const bool in_smem = quads_in_smem(m);
   auto kernel = in_smem ? frontend_kernel<true> : frontend_kernel<false>;
   const size_t smem = frontend_smem_bytes(m);
-  static thread_local size_t configured[2] = {0, 0};
-  if (configured[in_smem] < smem) {
-    KWS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured[in_smem] = smem;
-  }
+  // the attribute is per device: set it on every launch (a few hundred ns), never cached per thread
+  KWS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   KWS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFeThreads, smem));
   if (per_sm < 1) return fail(KWS_ERR_CUDA, "frontend_kernel does not fit on an SM (smem %zu)", smem);

@@ -49,7 +49,6 @@ constexpr int kTcEpiWarps = 16;           // warps 0-15: gate algebra.  Warp w o
 constexpr int kTcEpiThreads = 32 * kTcEpiWarps;   //   and the 32 hidden units [32*(w/4), +32) of those streams
 constexpr int kTcThreads = kTcEpiThreads + 128;   // + warpgroup 4: warp 16 issues the MMAs (warps 17-19 only donate registers)
 constexpr int kTcUnits = 32;              // hidden units per gate thread
-constexpr int kTcMaxClasses = 8;          // FC columns kept per thread
 
 
 struct GruTcParams {
@@ -690,6 +689,9 @@ void pack_tc_weights(const float* gates_kernel, const float* cand_kernel, int in
 
 int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
   if (a.S <= 0) return KWS_OK;
+  if (m->cfg.num_classes > kTcMaxClasses)
+    return fail(KWS_ERR_UNSUPPORTED, "the tensor-core recurrent kernel keeps %d classes, the model has %d", kTcMaxClasses,
+                m->cfg.num_classes);
   const int L = m->cfg.num_layers;
   if (a.n <= 0) {
     if (a.state_out != a.state_in)

@@ -13,13 +13,16 @@
 // The window keeps, per frame, only what ctc_decode2 consumes: the above-threshold winner
 // column or -1 (one byte), so re-decoding the 450-frame window every chunk costs 480 B of
 // reads per stream instead of 10.8 KB of fp32 probabilities.
+#include <atomic>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 #include "decode_core.cuh"
 
 struct kws_stream {
   kws_model* model = nullptr;
+  int device = 0;           // cached: destroy must not dereference the model (it may already be gone)
   kws_stream_config cfg;
   int64_t S = 0;
   int max_frames = 0;       // frames a chunk of cfg.max_chunk samples can produce
@@ -256,6 +259,7 @@ extern "C" int kws_stream_create(kws_model* m, const kws_stream_config* cfg, kws
   KWS_CUDA_OK(cudaSetDevice(m->device));
   kws_stream* st = new kws_stream();
   st->model = m;
+  st->device = m->device;
   st->cfg = *cfg;
   st->S = cfg->n_streams;
   st->max_frames = mf;
@@ -290,7 +294,7 @@ extern "C" int kws_stream_create(kws_model* m, const kws_stream_config* cfg, kws
 extern "C" int kws_stream_destroy(kws_stream* st) {
   clear_error();
   if (st) {
-    cudaSetDevice(st->model->device);
+    cudaSetDevice(st->device);
     cudaDeviceSynchronize();
     free_stream(st);
   }
@@ -325,11 +329,13 @@ extern "C" int kws_stream_copy_state(kws_stream* st, float* state_out, void* str
 
 // Debug: device time of the three parts of a step (front end incl. the fused pre-step | GRU layers | decode + trigger),
 // measured with CUDA events on the step's stream.  Enabling it makes every step synchronise -- never on in production.
-static int g_step_timing_on = 0;
+static std::atomic<int> g_step_timing_on{0};
+static std::mutex g_step_mutex;                    // the sums may be fed by stream objects on several host threads
 static double g_step_ms[3] = {0.0, 0.0, 0.0};
 static long g_step_count = 0;
 extern "C" int kws_debug_step_timing(int enable, double* ms_out3, long long* steps_out) {
   kws::clear_error();
+  std::lock_guard<std::mutex> lock(g_step_mutex);
   if (ms_out3) {
     for (int i = 0; i < 3; ++i) ms_out3[i] = g_step_ms[i];
   }
@@ -428,6 +434,7 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
     KWS_CUDA_OK(cudaEventRecord(tev[3], cs));
     KWS_CUDA_OK(cudaEventSynchronize(tev[3]));
     if (n_step > 0) {
+      std::lock_guard<std::mutex> lock(g_step_mutex);
       for (int i = 0; i < 3; ++i) {
         float ms = 0.0f;
         KWS_CUDA_OK(cudaEventElapsedTime(&ms, tev[i], tev[i + 1]));

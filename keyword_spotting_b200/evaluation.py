@@ -43,8 +43,10 @@ def evaluate_softmax(softmax, correctness, lens=None, label_seqs: str = "1233", 
     _, _, trig = prediction.decode_batch(softmax, lens=lens, mode=prediction.MODE_CTC_DECODE, keyword=label_seqs,
                                          device=device, want_labels=False)
     trig_t = trig if isinstance(trig, torch.Tensor) else torch.from_numpy(np.asarray(trig))
-    tgt = _tensors.to_device(np.asarray(correctness, np.int32), torch.int32, trig_t.device) if trig_t.is_cuda \
-        else torch.from_numpy(np.asarray(correctness, np.int32))
+    if isinstance(correctness, torch.Tensor):
+        tgt = correctness.to(device=trig_t.device, dtype=torch.int32)
+    else:
+        tgt = torch.from_numpy(np.asarray(correctness, np.int32)).to(trig_t.device)
     if tgt.shape != trig_t.shape:
         raise _lib.InvalidArgumentError("correctness must have one entry per utterance")
     xor = tgt ^ trig_t                                     # utils/prediction.py:203-210

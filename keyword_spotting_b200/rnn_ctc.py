@@ -186,8 +186,7 @@ class DeployModel:
                  (not isinstance(pcm, torch.Tensor) and np.asarray(pcm).dtype == np.int16)
         dt = torch.int16 if is_i16 else torch.float32
         x = _tensors.to_device(pcm, dt, self.device)
-        squeeze = x.dim() == 1
-        if squeeze:
+        if x.dim() == 1:
             x = x.unsqueeze(0)                      # tf.expand_dims(inputX, 0), rnn_ctc.py:134
         if x.dim() != 2:
             raise _lib.InvalidArgumentError("inputX must be [L] or [S, L]")
@@ -240,7 +239,9 @@ class DeployModel:
             raise _lib.InvalidArgumentError("mel must be [n, %d] or [S, n, %d]" % (self.config.n_mel, self.config.n_mel))
         S, n, _ = x.shape
         st_in = self._prep_state(rnn_initial_states, S)
-        sl = None if seq_len is None else _tensors.to_device(np.asarray(seq_len, np.int32), torch.int32, self.device)
+        sl = None if seq_len is None else _tensors.to_device(seq_len, torch.int32, self.device)
+        if sl is not None and tuple(sl.shape) != (S,):
+            raise _lib.InvalidArgumentError("seq_len must be [%d], got %r" % (S, tuple(sl.shape)))
         C = self.config.num_classes
         probs = torch.empty((S, n, C), dtype=torch.float32, device=self.device)
         logits = torch.empty_like(probs) if want_logits else None
@@ -265,9 +266,7 @@ class DeployModel:
                 raise _lib.InvalidArgumentError("unknown fetch %r; the frozen graph exposes %s" % (nme, sorted(known)))
         if INPUT_X not in feed_dict or INITIAL_STATES not in feed_dict:
             raise _lib.InvalidArgumentError("feed_dict must hold %r and %r" % (INPUT_X, INITIAL_STATES))
-        x = feed_dict[INPUT_X]
-        one_d = (x.dim() if isinstance(x, torch.Tensor) else np.asarray(x).ndim) == 1
-        outs = self.forward(x, feed_dict[INITIAL_STATES], want_logits=LOGIT in names)
+        outs = self.forward(feed_dict[INPUT_X], feed_dict[INITIAL_STATES], want_logits=LOGIT in names)
         by_name = {SOFTMAX: outs[0], RNN_STATES: outs[1]}
         if LOGIT in names:
             by_name[LOGIT] = outs[2]

@@ -33,7 +33,7 @@ def decode_batch(softmax, lens=None, mode=MODE_CTC_DECODE, lockout=3, thres=None
     S, T, C = p.shape
     if max_labels is None:
         max_labels = 2 * T + 1
-    ln = None if lens is None else _tensors.to_device(np.asarray(lens, np.int32), torch.int32, dev)
+    ln = None if lens is None else _tensors.to_device(lens, torch.int32, dev)
     labels = torch.empty((S, max_labels), dtype=torch.int32, device=dev) if want_labels else None
     counts = torch.empty((S,), dtype=torch.int32, device=dev)
     trig = torch.empty((S,), dtype=torch.int32, device=dev)
@@ -63,16 +63,25 @@ def ctc_decode(softmax, lockout=3, thres=0.5, loose_thres=0.2):
     return _single(softmax, MODE_CTC_DECODE, lockout=lockout, thres=thres, loose_thres=loose_thres)
 
 
+def _label_columns(softmax, classnum):
+    """The reference slices ``softmax[:, 1:classnum-1]`` (utils/prediction.py:67,91); numpy clamps the end to the
+    actual column count, so ``classnum`` larger than the array keeps the LAST column too.  The device decoder
+    reads columns ``1..C-2`` of what it is given: hand it the kept columns plus one unused closing column."""
+    sm = np.asarray(softmax, dtype=np.float32)
+    if sm.ndim != 2:
+        raise _lib.InvalidArgumentError("softmax must be [T, C]")
+    end = max(1, min(int(classnum) - 1, sm.shape[1]))
+    return np.concatenate([sm[:, :end], np.zeros((sm.shape[0], 1), np.float32)], axis=1)
+
+
 def ctc_decode2(softmax, classnum, thres=0.4):
     """utils/prediction.py:65-86 (the streaming decoder of detector.py:200)."""
-    sm = np.asarray(softmax, dtype=np.float32)
-    return _single(sm[:, :classnum], MODE_CTC_DECODE2, thres=thres)
+    return _single(_label_columns(softmax, classnum), MODE_CTC_DECODE2, thres=thres)
 
 
 def ctc_decode_strict(softmax, classnum, lockout=3, thres=0.5):
     """utils/prediction.py:89-108."""
-    sm = np.asarray(softmax, dtype=np.float32)
-    return _single(sm[:, :classnum], MODE_CTC_DECODE_STRICT, lockout=lockout, thres=thres)
+    return _single(_label_columns(softmax, classnum), MODE_CTC_DECODE_STRICT, lockout=lockout, thres=thres)
 
 
 def ctc_predict(seq, label="1233"):

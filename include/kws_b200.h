@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define KWS_B200_ABI_VERSION 1
+#define KWS_B200_ABI_VERSION 2
 
 typedef enum kws_status {
   KWS_OK = 0,
@@ -199,6 +199,50 @@ int kws_stream_copy_state(kws_stream* st, float* state_out, void* stream);
 /* Window decode of every stream as of the last step (labels as kws_ctc_decode). */
 int kws_stream_labels(kws_stream* st, int32_t* labels_out, int32_t max_labels,
                       int32_t* counts_out, void* stream);
+
+/* ----------------------------------------------------------------- wave server
+ * The serving loop itself (HotwordDetector.start, detector.py:148-212: read a chunk -> model -> decode -> react,
+ * forever) for all the streams of one GPU.  The streams are split into `waves` equal groups; a wave is one
+ * kws_stream with its own CUDA stream, two pinned HOST ingest slots and, captured at creation, a CUDA graph of the
+ * whole chunk:  H2D(pcm) -> front end -> GRU x layers -> decode/trigger -> D2H(trigger flags).  Serving a wave's
+ * chunk is one graph launch; waves overlap each other's copies and kernels; a chunk's latency (host clock, submit ->
+ * trigger flags visible on the host) is recorded for every (wave, chunk).  One host thread drives a server.       */
+typedef struct kws_server kws_server;
+
+typedef struct kws_server_config {
+  int64_t n_streams;       /* streams served by this GPU; a multiple of `waves`            */
+  int32_t waves;           /* 16: groups served independently                               */
+  int32_t chunk_samples;   /* 4800 = 300 ms (README.md:88, detector.py:150)                 */
+  int32_t use_graphs;      /* 1: replay CUDA graphs; 0: enqueue copies and kernels directly */
+  kws_stream_config stream;/* window / VAD / threshold / keyword (n_streams, max_chunk ignored) */
+} kws_server_config;
+
+int kws_server_create(kws_model* m, const kws_server_config* cfg, kws_server** out);
+int kws_server_destroy(kws_server* s);
+int kws_server_info(const kws_server* s, int64_t* streams_per_wave, int32_t* waves, int32_t* graphs);
+/* Forget GRU state, tails and windows of every stream (nothing may be in flight). */
+int kws_server_reset(kws_server* s);
+/* Pinned HOST buffer [streams_per_wave, chunk_samples] int16 that the NEXT kws_server_submit(wave) will send:
+ * the producer (network / audio threads) writes the wave's chunk here.  At most two chunks per wave are in
+ * flight, so the slot returned after a submit is free as soon as the chunk before last has been waited for.   */
+int16_t* kws_server_ingest_slot(kws_server* s, int32_t wave);
+/* Enqueue the wave's chunk (non-blocking). */
+int kws_server_submit(kws_server* s, int32_t wave);
+/* Block until the wave's oldest chunk in flight is done.  *trigger_host: pinned HOST flags [streams_per_wave]
+ * (1 = keyword fired in this chunk; valid until two more submits of the wave); *latency_ms: submit -> now.     */
+int kws_server_wait(kws_server* s, int32_t wave, const int32_t** trigger_host, double* latency_ms);
+/* `rounds` chunks for every wave from the ingest slots as they are, wave by wave, at most `depth` waves in flight
+ * (the steady-state loop of a server whose producers keep the slots filled).                                   */
+int kws_server_serve(kws_server* s, int32_t rounds, int32_t depth);
+/* Latency percentiles over the chunks completed since the last reset of the statistics, their number, and the
+ * number of triggers they raised.  Any output may be NULL.                                                     */
+int kws_server_stats(kws_server* s, int reset, double* p50_ms, double* p99_ms, double* max_ms, int64_t* chunks,
+                     int64_t* triggers);
+/* 1: submit only moves the bytes (H2D of the slot, D2H of the flags) -- the link ceiling of this box for the
+ * same buffers, CUDA streams and schedule.  Nothing may be in flight when switching.                           */
+int kws_server_set_copy_only(kws_server* s, int copy_only);
+/* The wave's stream object (for kws_stream_labels / kws_stream_copy_state); owned by the server. */
+kws_stream* kws_server_wave_stream(kws_server* s, int32_t wave);
 
 /* ----------------------------------------------------------------- octbit
  * K5 -- OctbitMatMul (octbit/octbit_mat_mul_op.cc:49-183; Python wrapper

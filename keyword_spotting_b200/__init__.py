@@ -7,7 +7,7 @@ CPU fallback anywhere in this package.
 
 Reference entry point                         -> here
   models/rnn_ctc.py       DeployModel          rnn_ctc.DeployModel
-  detector.py             HotwordDetector.start streaming.StreamingDetector
+  detector.py             HotwordDetector.start streaming.StreamingDetector (one batch), serving.WaveServer (a GPU's streams)
   utils/prediction.py     ctc_decode* / predict utils.prediction
   octbit/octbit_ops.py    octbit_mat_mul       octbit.octbit_ops.octbit_mat_mul
   octbit/octbit_graph.py  octize_weight_int8.. octbit.octbit_graph.octize_weight_int8_signed
@@ -22,8 +22,9 @@ from ._lib import InvalidArgumentError, KwsCudaError  # noqa: E402
 from .config import Config, get_config  # noqa: E402
 from .rnn_ctc import DeployModel, ModelWeights  # noqa: E402
 from .streaming import StreamingDetector  # noqa: E402
+from .serving import WaveServer  # noqa: E402
 from .attention_ctc import AttentionConfig, AttentionDeployModel, AttentionWeights  # noqa: E402
 
-__all__ = ["Config", "get_config", "DeployModel", "ModelWeights", "StreamingDetector",
+__all__ = ["Config", "get_config", "DeployModel", "ModelWeights", "StreamingDetector", "WaveServer",
            "AttentionConfig", "AttentionDeployModel", "AttentionWeights",
            "InvalidArgumentError", "KwsCudaError"]

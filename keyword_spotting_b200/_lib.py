@@ -53,6 +53,11 @@ class StreamConfig(Structure):
                 ("vad_threshold", c_int32), ("decode_thres", c_double), ("keyword", c_char * 20)]
 
 
+class ServerConfig(Structure):
+    _fields_ = [("n_streams", c_int64), ("waves", c_int32), ("chunk_samples", c_int32), ("use_graphs", c_int32),
+                ("stream", StreamConfig)]
+
+
 class AttentionConfig(Structure):
     _fields_ = [(n, c_int32) for n in ("n_mel", "combine_frame", "hidden", "heads", "num_layers", "ffn",
                                        "num_classes", "use_relu")]
@@ -92,6 +97,18 @@ _SIGNATURES = {
     "kws_stream_state": (c_void_p, [c_void_p]),
     "kws_stream_copy_state": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kws_stream_labels": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "kws_server_create": (c_int, [c_void_p, POINTER(ServerConfig), POINTER(c_void_p)]),
+    "kws_server_destroy": (c_int, [c_void_p]),
+    "kws_server_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]),
+    "kws_server_reset": (c_int, [c_void_p]),
+    "kws_server_ingest_slot": (c_void_p, [c_void_p, c_int32]),
+    "kws_server_submit": (c_int, [c_void_p, c_int32]),
+    "kws_server_wait": (c_int, [c_void_p, c_int32, POINTER(c_void_p), POINTER(c_double)]),
+    "kws_server_serve": (c_int, [c_void_p, c_int32, c_int32]),
+    "kws_server_stats": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_double),
+                                 POINTER(c_int64), POINTER(c_int64)]),
+    "kws_server_set_copy_only": (c_int, [c_void_p, c_int]),
+    "kws_server_wave_stream": (c_void_p, [c_void_p, c_int32]),
     "kws_octbit_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "kws_octbit_matmul": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int64, c_int64,
                                   c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),

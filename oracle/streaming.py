@@ -86,12 +86,18 @@ class StreamOracle:
         self.res = np.zeros((n_streams, 0), dtype=np.float32)   # same length for all streams
         self.queues = [SimpleQueue(window) for _ in range(n_streams)]
 
-    def step(self, chunk_i16: np.ndarray):
+    def step(self, chunk_i16: np.ndarray, decide_on=None):
         """One chunk ``[S, n_new]`` int16 for every stream.
 
         Returns dict: ``speech`` bool[S], ``softmax`` f[S, n, C], ``trigger``
         int32[S], ``labels`` list of int32 arrays (window decode per stream),
         ``state`` (after trigger reset).
+
+        ``decide_on``: optional callable ``softmax -> softmax`` applied to what
+        enters the decision window (the returned ``softmax`` stays the oracle's
+        own).  The parity tests use it to take the frames whose decision lies
+        within the float tolerance of a threshold (``ambiguous_frames``) from the
+        implementation under test, so that everything else must match bit for bit.
         """
         chunk_i16 = np.asarray(chunk_i16, dtype=np.int16)
         assert chunk_i16.shape[0] == self.S
@@ -110,9 +116,10 @@ class StreamOracle:
         self.state = state
         trigger = np.zeros(self.S, dtype=np.int32)
         labels = []
+        decided = softmax if decide_on is None else decide_on(softmax)
         for s in range(self.S):
             q = self.queues[s]
-            q.add(softmax[s])
+            q.add(decided[s])
             window = np.concatenate(q.get_all(), axis=0)
             seq = op.ctc_decode2(window, self.w.num_classes, self.decode_thres)
             labels.append(seq)
@@ -122,6 +129,18 @@ class StreamOracle:
                 self.state[:, s, :] = 0
         return dict(speech=speech, softmax=softmax, trigger=trigger, labels=labels,
                     state=self.state.copy())
+
+
+def ambiguous_frames(softmax: np.ndarray, thres: float, tol: float) -> np.ndarray:
+    """bool ``[S, n]``: frames whose ``ctc_decode2`` token (utils/prediction.py:71-84: above-threshold winner of
+    columns ``1..C-2``, else none) can differ between two softmax arrays that agree within ``tol`` (max-abs):
+    the winner is within ``tol`` of the threshold, or it is above ``thres - tol`` and the runner-up is within
+    ``2 tol`` of it.  For every other frame a ``tol``-close softmax yields the identical token."""
+    lab = np.asarray(softmax, dtype=np.float64)[..., 1:-1]
+    top = np.sort(lab, axis=-1)
+    m1 = top[..., -1]
+    m2 = top[..., -2] if lab.shape[-1] > 1 else np.full_like(m1, -np.inf)
+    return (np.abs(m1 - thres) <= tol) | ((m1 > thres - tol) & (m1 - m2 <= 2 * tol))
 
 
 def stream_vs_offline(pcm_f32: np.ndarray, weights: om.Weights, seg_len=3600, dtype=np.float32):

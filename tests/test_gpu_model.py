@@ -293,12 +293,15 @@ def test_config2_full_size_properties(precision):
     dm.close()
 
 
-def test_streaming_server_tensor_core_mode():
-    """The default (tensor-core) server against the detector-loop oracle.  Probabilities and state within the
-    1e-3 contract; the decode/trigger logic is integer-exact GIVEN the probabilities, which is checked by
-    replaying the GPU's own probabilities through the reference-pinned decoders."""
+def test_streaming_server_tensor_core_mode(capsys):
+    """The default (tensor-core) server against the detector-loop oracle with the reference's own (un-boosted)
+    random-init FC and a threshold low enough (0.2) that labels appear.  Probabilities and state within the 1e-3
+    contract; triggers and window labels bit-identical to the fp32 oracle for every stream and chunk, the frames
+    whose decision lies within the tolerance of the threshold being taken from the GPU
+    (tests/test_gpu_parity_scale.py states the rule) -- no stream is masked out."""
     from keyword_spotting_b200 import DeployModel, StreamingDetector
-    from oracle import model as om, prediction as op, streaming as ost
+    from oracle import model as om, streaming as ost
+    from tests.test_gpu_parity_scale import _MarginJudge, _check_chunk
     ow = om.init_weights(seed=1234, n_mel=40)
     dm = DeployModel(make_config(40), to_product_weights(ow))          # precision="tc" is the default
     assert dm.precision == "tc"
@@ -308,45 +311,25 @@ def test_streaming_server_tensor_core_mode():
     quiet = rng.random((S, chunks)) < 0.3
     for s, c in zip(*np.nonzero(quiet)):
         pcm[s, c * chunk:(c + 1) * chunk] = rng.integers(-2, 3, chunk)
-    # a threshold low enough that random-init posteriors produce labels, so the window logic is exercised
     det = StreamingDetector(dm, S, keyword="12", decode_thres=0.2)
     orc = ost.StreamOracle(ow, S, label="12", decode_thres=0.2)
-    windows = [ost.SimpleQueue(15) for _ in range(S)]
-    worst_p = worst_s = 0.0
-    n_lab = n_trig = 0
+    judge = _MarginJudge(0.2)
+    n_lab = 0
     for c in range(chunks):
         blk = pcm[:, c * chunk:(c + 1) * chunk]
-        want = orc.step(blk)
         trig, probs, nfr = det.step(blk, want_probs=True)
-        n = want["softmax"].shape[1]
-        assert (nfr == n).all()
         st = det.state().cpu().numpy()
         labels, counts = det.window_labels()
-        for s in range(S):
-            if not want["speech"][s]:
-                windows[s].clear()
-            windows[s].add(probs[s, :n])
-            seq = op.ctc_decode2(np.concatenate(windows[s].get_all(), 0), 6, 0.2)
-            fired = op.ctc_predict(seq, "12")
-            assert trig[s] == fired, (c, s)
-            if fired:
-                windows[s].clear()
-                assert counts[s] == 1
-            else:
-                np.testing.assert_array_equal(labels[s, :counts[s]], seq)
-                n_lab += len(seq) // 2
-            n_trig += fired
-        # numerical agreement with the fp32 oracle for the streams whose discrete history agrees
-        same = trig == want["trigger"]
-        worst_p = max(worst_p, float(np.abs(probs[same, :n] - want["softmax"][same]).max()))
-        worst_s = max(worst_s, float(np.abs(st[:, same] - want["state"][:, same]).max()))
-        # keep the oracle on the GPU's discrete trajectory so later chunks stay comparable
-        for s in np.nonzero(~same)[0]:
-            orc.state[:, s, :] = st[:, s, :]
-            if trig[s]:
-                orc.queues[s].clear()
-    assert worst_p < TOL_CONTRACT and worst_s < TOL_CONTRACT, (worst_p, worst_s)
+        judge.gpu = probs
+        want = orc.step(blk, decide_on=judge)
+        assert (nfr == want["softmax"].shape[1]).all()
+        _check_chunk(want, trig, probs, labels, counts, st, c)
+        n_lab += sum(len(l) // 2 for l in want["labels"])
+    frac = judge.ambiguous / judge.frames
+    with capsys.disabled():
+        print("\n[tc server, reference FC] ambiguous frames %d / %d = %.4f%%" % (judge.ambiguous, judge.frames, 100 * frac))
     assert n_lab > 50, n_lab
+    assert frac < 0.02
     det.close()
     dm.close()
 

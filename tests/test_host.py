@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libkws_b200.so does not export %s" % n
     assert sorted(_lib.EXPORTED_SYMBOLS) == names        # the ctypes table binds exactly the header
-    assert lib.kws_abi_version() == 1
+    assert lib.kws_abi_version() == 2
 
 
 def test_library_is_sm100a_only():

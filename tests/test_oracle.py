@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import cref, model as om, octbit as ooct, posenc as ope, prediction as op, streaming as ost
-from tests._util import golden, unpack
+from tests._util import golden, synth_pcm16, unpack
 
 
 # ---------------------------------------------------------------- decoders (utils/prediction.py)
@@ -285,3 +285,52 @@ def test_wer_oracle_matches_reference_golden():
     got = np.asarray([ow.wer(r, h) for r, h in zip(refs, hyps)])
     np.testing.assert_array_equal(got, g["wer"])
     assert max(len(r) for r in refs) == 254          # the reference's uint8 limit is covered
+
+
+def test_ambiguous_frames_cover_every_possible_token_flip():
+    """oracle.streaming.ambiguous_frames: for any two softmax arrays within `tol` of each other the ctc_decode2 token
+    (above-threshold winner of the label columns, else none) may differ ONLY at frames flagged ambiguous."""
+    from oracle import streaming as ost
+    rng = np.random.default_rng(11)
+    tol, thres = 1e-3, 0.4
+    n_flip = 0
+    for trial in range(40):
+        logits = rng.standard_normal((64, 30, 6)) * rng.uniform(0.5, 4.0)
+        # crowd many frames around the threshold / around ties
+        p = np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)
+        p[::3, :, 1] = thres + rng.uniform(-3 * tol, 3 * tol, p[::3, :, 1].shape)
+        p[1::3, :, 2] = p[1::3, :, 1] + rng.uniform(-4 * tol, 4 * tol, p[1::3, :, 1].shape)
+        p = p.astype(np.float32)
+        q = (p + rng.uniform(-tol, tol, p.shape) * 0.999).astype(np.float32)
+
+        def token(a):
+            lab = a[..., 1:-1].astype(np.float64)
+            return np.where(lab.max(-1) > thres, lab.argmax(-1), -1)
+
+        flip = token(p) != token(q)
+        amb = ost.ambiguous_frames(p, thres, tol)
+        assert not (flip & ~amb).any()
+        n_flip += int(flip.sum())
+    assert n_flip > 100        # the construction really produces flips
+
+
+def test_stream_oracle_decide_on_hook_only_changes_the_decision_window():
+    from oracle import model as om, streaming as ost
+    ow = om.init_weights(seed=1234, n_mel=40)
+    ow.fc_w = (ow.fc_w * 6).astype(np.float32)
+    rng = np.random.default_rng(5)
+    pcm = synth_pcm16(rng, 6, 4800 * 3, silent_frac=0.0)
+    a, b = ost.StreamOracle(ow, 6, label="1"), ost.StreamOracle(ow, 6, label="1")
+    for c in range(3):
+        blk = pcm[:, c * 4800:(c + 1) * 4800]
+        ra = a.step(blk)
+        rb = b.step(blk, decide_on=lambda sm: sm.copy())             # identity hook: identical run
+        np.testing.assert_array_equal(ra["trigger"], rb["trigger"])
+        np.testing.assert_array_equal(ra["softmax"], rb["softmax"])
+    never = ost.StreamOracle(ow, 6, label="1")
+    fired = 0
+    for c in range(3):
+        r = never.step(pcm[:, c * 4800:(c + 1) * 4800], decide_on=lambda sm: np.zeros_like(sm))
+        fired += int(r["trigger"].sum())
+        assert r["softmax"].max() > 0.1                              # the returned softmax stays the oracle's own
+    assert fired == 0

@@ -475,6 +475,26 @@ def ops_block(args, torch, device, peaks):
     rec["speedup_vs_cpu"] = rec["utterances_per_s"] / rec["cpu_baseline"]["utterances_per_s"]
     out["offline_config2_S4096_3s"] = rec
     del pcm16, st0
+    # ---- BASELINE configs[3] as a model: the octbit-rewritten graph (float cell_0, OctbitMatMul for cell_1 and the FC),
+    # one 300 ms chunk for 131,072 streams, PCM resident in HBM; CPU: the oracle loop over the UNMODIFIED reference op
+    from keyword_spotting_b200 import OctbitModelWeights
+    dm.set_octbit(OctbitModelWeights.from_float(wts))
+    S3 = 131072
+    pcm3 = (torch.randn((S3, 5120), device=device, generator=g) * 800).clamp_(-32768, 32767).to(torch.int16)
+    st3 = torch.zeros((2, S3, 128), device=device)
+    ms = timeit(lambda: dm(pcm3, st3), iters=3, warm=1)
+    rec = dict(ms=ms, audio_s_per_s=0.3 * S3 / ms * 1e3,
+               workload="configs[3]: graph_octbit.pb forward, 131072 streams x one 300 ms chunk (30 frames), per-stream activation "
+                        "ranges (the reference's batch-1 semantics)")
+    octw = om.octize_model(ow)
+    nb3 = 4
+    pc3 = om.pcm16_to_float(pcm3[:nb3].cpu().numpy())
+    t = cpu_time(lambda: om.octbit_deploy_forward(pc3, np.zeros((2, nb3, 128), np.float32), ow, octw), min_s=2.0)
+    rec["cpu_baseline"] = dict(audio_s_per_s=0.3 * nb3 / t, kind="reference op inside the oracle loop", cores=1,
+                               sample="%d streams x 30 frames: numpy graph around the unmodified octbit_mat_mul_op.cc (oracle/_ref)" % nb3)
+    rec["speedup_vs_cpu"] = rec["audio_s_per_s"] / rec["cpu_baseline"]["audio_s_per_s"]
+    out["octbit_graph_S131072_chunk"] = rec
+    del pcm3, st3
     dm.close()
     # ---- BASELINE configs[4]: attention_ctc forward, batched 8 s utterances (mel [B, 798, 60] -> T' = 400)
     am = AttentionDeployModel(AttentionConfig(), device=device)

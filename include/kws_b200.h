@@ -94,6 +94,32 @@ int kws_model_destroy(kws_model* m);
 int kws_model_set_precision(kws_model* m, int precision);
 int kws_model_get_precision(const kws_model* m);
 
+/* The octbit-rewritten deployment graph (graph_octbit.pb: main.py:357-371, octbit/octbit_graph.py:461-536).  The
+ * rewriter turns every MatMul outside cell_0 into OctbitMatMul (octbit_graph.py:218-225): gates and candidate of the
+ * upper GRU layers ([in+H] -> 2H and -> H) and the FC (H -> C); cell_0, the mel projection and every BiasAdd /
+ * activation stay float.  HOST pointers per converted MatMul: the qint8 Const [out, in] (already transposed), the
+ * op's `scale` attr and its `bias` attr [out] (octbit_graph.py:191-215, 527-536).  NULL = that MatMul stays float.
+ * The op quantises its input with the min / max of the WHOLE call (octbit_mat_mul_op.cc:90-124); the reference
+ * deploys at batch 1, so the range is per stream -- per time step for the GRU MatMuls, per chunk (all frames of the
+ * call) for the FC -- and that is what the batched kernels reproduce: S independent batch-1 graphs.
+ * After this call every forward of the model (kws_gru_forward, kws_deploy_forward, kws_stream_step, the wave
+ * server) runs the octbit graph; NULL switches back to the float graph.  Stream objects created BEFORE the switch
+ * share one model-owned scratch and must then be stepped from a single CUDA stream.                            */
+typedef struct kws_octbit_weights {
+  const int8_t* gates_wq[4];     /* [2H, in+H] */
+  float gates_scale[4];
+  const float* gates_obias[4];   /* [2H] */
+  const int8_t* cand_wq[4];      /* [H, in+H] */
+  float cand_scale[4];
+  const float* cand_obias[4];    /* [H] */
+  const int8_t* fc_wq;           /* [C, H] */
+  float fc_scale;
+  const float* fc_obias;         /* [C] */
+} kws_octbit_weights;
+
+int kws_model_set_octbit(kws_model* m, const kws_octbit_weights* w);
+int kws_model_is_octbit(const kws_model* m);
+
 /* utils/stft.py:60-61: 1 + floor((L - fft)/hop); <= 0 when L < fft. */
 int kws_num_frames(const kws_model* m, int64_t signal_length);
 

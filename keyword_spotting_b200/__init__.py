@@ -20,11 +20,11 @@ _lib_mod.load()          # fail loudly at import if the CUDA library cannot be b
 
 from ._lib import InvalidArgumentError, KwsCudaError  # noqa: E402
 from .config import Config, get_config  # noqa: E402
-from .rnn_ctc import DeployModel, ModelWeights  # noqa: E402
+from .rnn_ctc import DeployModel, ModelWeights, OctbitMatrix, OctbitModelWeights  # noqa: E402
 from .streaming import StreamingDetector  # noqa: E402
 from .serving import WaveServer  # noqa: E402
 from .attention_ctc import AttentionConfig, AttentionDeployModel, AttentionWeights  # noqa: E402
 
-__all__ = ["Config", "get_config", "DeployModel", "ModelWeights", "StreamingDetector", "WaveServer",
+__all__ = ["Config", "get_config", "DeployModel", "ModelWeights", "OctbitMatrix", "OctbitModelWeights", "StreamingDetector", "WaveServer",
            "AttentionConfig", "AttentionDeployModel", "AttentionWeights",
            "InvalidArgumentError", "KwsCudaError"]

@@ -44,6 +44,12 @@ class ModelWeights(Structure):
                 ("fc_w", c_void_p), ("fc_b", c_void_p)]
 
 
+class OctbitWeights(Structure):
+    _fields_ = [("gates_wq", c_void_p * 4), ("gates_scale", c_float * 4), ("gates_obias", c_void_p * 4),
+                ("cand_wq", c_void_p * 4), ("cand_scale", c_float * 4), ("cand_obias", c_void_p * 4),
+                ("fc_wq", c_void_p), ("fc_scale", c_float), ("fc_obias", c_void_p)]
+
+
 class DecodeParams(Structure):
     _fields_ = [("mode", c_int32), ("lockout", c_int32), ("thres", c_double), ("loose_thres", c_double)]
 
@@ -78,6 +84,8 @@ _SIGNATURES = {
     "kws_model_destroy": (c_int, [c_void_p]),
     "kws_model_set_precision": (c_int, [c_void_p, c_int]),
     "kws_model_get_precision": (c_int, [c_void_p]),
+    "kws_model_set_octbit": (c_int, [c_void_p, POINTER(OctbitWeights)]),
+    "kws_model_is_octbit": (c_int, [c_void_p]),
     "kws_num_frames": (c_int, [c_void_p, c_int64]),
     "kws_model_reserve": (c_int, [c_void_p, c_int64, c_int32]),
     "kws_frontend_mel": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),

@@ -76,6 +76,7 @@ static void free_model(kws_model* m) {
   if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
   cudaFree(m->scratch_mel);
   cudaFree(m->scratch_seq);
+  free_octbit(m);
   delete m;
 }
 
@@ -188,6 +189,7 @@ extern "C" int kws_model_get_precision(const kws_model* m) { return m ? m->preci
 
 namespace kws {
 int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st) {
+  if (m->octbit) return launch_gru_octbit(m, a, st);
   return model_uses_tc(m) ? launch_gru_tc(m, a, st) : launch_gru_fp32(m, a, st);
 }
 }  // namespace kws

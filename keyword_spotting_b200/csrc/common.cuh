@@ -64,6 +64,15 @@ struct LayerWeights {
   float* tc_bias = nullptr;
 };
 
+struct OctbitMatrix {           // one OctbitMatMul's constants on the device (gru_octbit.cu)
+  signed char* wq = nullptr;    // [B, K] int8, already transposed (octbit_graph.py:191-215)
+  float* obias = nullptr;       // [B] the op's bias attr
+  float scale = 0.0f;           // the op's scale attr
+  int* cand_count = nullptr;    // [B] pairs of the row that can saturate int16
+  unsigned short* cand = nullptr;   // [B, K/2]
+  int B = 0, K = 0;
+};
+
 struct alignas(16) MelQuad {     // 4 consecutive bins (from an even bin) of one mel band
   float w[4];
   int mag_off;                   // byte offset of the bin pair's row in the front end's transposed magnitude array
@@ -93,6 +102,11 @@ struct kws_model {
   int32_t cap_frames = 0;
   float* scratch_mel = nullptr;   // [S, n, M]
   float* scratch_seq = nullptr;   // layer hand-off [tiles, n, H, 64]
+  // the octbit-rewritten graph (kws_model_set_octbit): per layer gates / candidate, and the FC
+  bool octbit = false;
+  kws::OctbitMatrix oct_gates[kws::kMaxLayers], oct_cand[kws::kMaxLayers], oct_fc;
+  float* oct_y_rows = nullptr;    // [S, n, H] last-layer outputs for the FC (non-stream forwards)
+  size_t oct_y_cap = 0;
   cudaStream_t aux_stream = nullptr;          // second stream + events of the layer pipeline for small batches (gru_tc.cu)
   std::vector<cudaEvent_t> aux_events;
 };
@@ -130,7 +144,7 @@ constexpr int kTcMaxClasses = 8;   // FC columns the tensor-core recurrent kerne
 // The tensor-core recurrent kernel serves models of up to kTcMaxClasses classes; wider FC layers run on the exact fp32
 // kernel whatever the requested precision (never a silently truncated softmax).
 inline bool model_uses_tc(const kws_model* m) {
-  return m->precision == KWS_PRECISION_TC_FP16 && m->cfg.num_classes <= kTcMaxClasses;
+  return !m->octbit && m->precision == KWS_PRECISION_TC_FP16 && m->cfg.num_classes <= kTcMaxClasses;
 }
 inline bool mel_can_tile(const kws_model* m) { return model_uses_tc(m) && m->cfg.n_mel % 4 == 0; }
 inline size_t mel_scratch_elems(int64_t S, int32_t n, int n_mel) {
@@ -152,6 +166,7 @@ struct GruArgs {
   float* probs = nullptr;                 // [S, n, C]
   float* logits = nullptr;                // [S, n, C] or null
   float* seq_scratch = nullptr;           // inter-layer hand-off of seq_scratch_elems() floats; null -> the model's own
+  float* y_rows_scratch = nullptr;        // octbit graph: [S, n, H] last-layer outputs for the FC; null -> the model's own
 };
 inline size_t seq_scratch_elems(int64_t S, int32_t n, int num_layers) {
   if (num_layers < 2) return 0;
@@ -160,5 +175,9 @@ inline size_t seq_scratch_elems(int64_t S, int32_t n, int num_layers) {
 int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st);        // dispatches on m->precision
 int launch_gru_fp32(kws_model* m, const GruArgs& a, cudaStream_t st);   // gru.cu   (exact fp32 FFMA)
 int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st);     // gru_tc.cu (tcgen05, fp16 operands)
+int launch_gru_octbit(kws_model* m, const GruArgs& a, cudaStream_t st); // gru_octbit.cu (the octbit-rewritten graph)
+int launch_gru_fp32_layer(kws_model* m, const GruArgs& a, int l, const float* x_tiled, float* y_tiled, float* y_rows,
+                          cudaStream_t st);                             // gru.cu: one fp32 layer without the FC
+void free_octbit(kws_model* m);
 
 }  // namespace kws

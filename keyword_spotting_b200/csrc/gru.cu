@@ -34,6 +34,7 @@ struct GruLayerParams {
   const float* x_rowmajor;      // [S, n, in_dim]
   const float* x_tiled;         // [tiles, n, in_dim(=H), 64]
   float* y_tiled;               // [tiles, n, H, 64] or null (last layer)
+  float* y_rows;                // [S, n, H] row-major or null (the octbit graph's FC reads the last layer from here)
   const float* wg;              // [in+H, 2H]
   const float* bg;              // [2H]
   const float* wc;              // [in+H, H]
@@ -240,11 +241,21 @@ gru_layer_kernel(const GruLayerParams p) {
         *reinterpret_cast<float4*>(Hs + (j0 + c) * kTs + s0 + 4) = make_float4(h[4][c], h[5][c], h[6][c], h[7][c]);
       }
       if (!kLast) {
-        float* dst = p.y_tiled + ((tile * p.n + t) * static_cast<long>(kH)) * kTs;
+        if (p.y_tiled) {
+          float* dst = p.y_tiled + ((tile * p.n + t) * static_cast<long>(kH)) * kTs;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          *reinterpret_cast<float4*>(dst + (j0 + c) * kTs + s0) = make_float4(y[0][c], y[1][c], y[2][c], y[3][c]);
-          *reinterpret_cast<float4*>(dst + (j0 + c) * kTs + s0 + 4) = make_float4(y[4][c], y[5][c], y[6][c], y[7][c]);
+          for (int c = 0; c < 4; ++c) {
+            *reinterpret_cast<float4*>(dst + (j0 + c) * kTs + s0) = make_float4(y[0][c], y[1][c], y[2][c], y[3][c]);
+            *reinterpret_cast<float4*>(dst + (j0 + c) * kTs + s0 + 4) = make_float4(y[4][c], y[5][c], y[6][c], y[7][c]);
+          }
+        }
+        if (p.y_rows) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long s = sbase + s0 + i;
+            if (s < p.S)
+              *reinterpret_cast<float4*>(p.y_rows + (s * p.n + t) * kH + j0) = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
+          }
         }
       } else {
         // outputs (zero past seq_len) -> RHs as the FC input; RHs is free until the next step's gates
@@ -307,6 +318,53 @@ static size_t gru_smem_bytes(int in_dim) {
                           kH * kMaxClasses + kMaxClasses + kTs * kMaxClasses);
 }
 
+// One layer of the fp32 path.  x_tiled: the layer below in the tiled hand-off layout (null for layer 0, which reads
+// a.x row-major); y_tiled / y_rows: where the layer's outputs go when it does not run the FC itself (either may be
+// null); fused_fc: the last layer of the float graph, FC + softmax in the same kernel.
+static int launch_layer_fp32(kws_model* m, const GruArgs& a, int l, const float* x_tiled, float* y_tiled, float* y_rows,
+                             bool fused_fc, cudaStream_t st) {
+  const long ntiles = ceil_div(a.S, kTs);
+  GruLayerParams p;
+  p.in_dim = m->layer[l].in_dim;
+  p.S = a.S;
+  p.n = a.n;
+  p.x_rowmajor = l == 0 ? a.x : nullptr;
+  p.x_tiled = l == 0 ? nullptr : x_tiled;
+  p.y_tiled = y_tiled;
+  p.y_rows = y_rows;
+  p.wg = m->layer[l].gates_kernel;
+  p.bg = m->layer[l].gates_bias;
+  p.wc = m->layer[l].cand_kernel;
+  p.bc = m->layer[l].cand_bias;
+  p.h_in = a.state_in + static_cast<long>(l) * a.S * kH;
+  p.h_out = a.state_out + static_cast<long>(l) * a.S * kH;
+  p.seq_len = a.seq_len;
+  p.zero_state = a.zero_state;
+  p.fc_w = m->fc_w;
+  p.fc_b = m->fc_b;
+  p.C = m->cfg.num_classes;
+  p.probs = a.probs;
+  p.logits = a.logits;
+  const size_t smem = gru_smem_bytes(p.in_dim);
+  long blocks = ntiles < sm_count() ? ntiles : sm_count();
+  if (fused_fc) {
+    KWS_CUDA_OK(cudaFuncSetAttribute(gru_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    gru_layer_kernel<true><<<static_cast<unsigned>(blocks), kGruThreads, smem, st>>>(p);
+  } else {
+    KWS_CUDA_OK(cudaFuncSetAttribute(gru_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    gru_layer_kernel<false><<<static_cast<unsigned>(blocks), kGruThreads, smem, st>>>(p);
+  }
+  KWS_LAUNCH_OK("gru_layer_kernel");
+  return KWS_OK;
+}
+
+int launch_gru_fp32_layer(kws_model* m, const GruArgs& a, int l, const float* x_tiled, float* y_tiled, float* y_rows,
+                          cudaStream_t st) {
+  return launch_layer_fp32(m, a, l, x_tiled, y_tiled, y_rows, false, st);
+}
+
 int launch_gru_fp32(kws_model* m, const GruArgs& a, cudaStream_t st) {
   if (a.S <= 0) return KWS_OK;
   const int L = m->cfg.num_layers;
@@ -329,38 +387,9 @@ int launch_gru_fp32(kws_model* m, const GruArgs& a, cudaStream_t st) {
   const long per_buf = ntiles * a.n * static_cast<long>(kH) * kTs;
   for (int l = 0; l < L; ++l) {
     const bool last = l == L - 1;
-    GruLayerParams p;
-    p.in_dim = m->layer[l].in_dim;
-    p.S = a.S;
-    p.n = a.n;
-    p.x_rowmajor = l == 0 ? a.x : nullptr;
-    p.x_tiled = l == 0 ? nullptr : seq + ((l - 1) & 1) * per_buf;
-    p.y_tiled = last ? nullptr : seq + (l & 1) * per_buf;
-    p.wg = m->layer[l].gates_kernel;
-    p.bg = m->layer[l].gates_bias;
-    p.wc = m->layer[l].cand_kernel;
-    p.bc = m->layer[l].cand_bias;
-    p.h_in = a.state_in + static_cast<long>(l) * a.S * kH;
-    p.h_out = a.state_out + static_cast<long>(l) * a.S * kH;
-    p.seq_len = a.seq_len;
-    p.zero_state = a.zero_state;
-    p.fc_w = m->fc_w;
-    p.fc_b = m->fc_b;
-    p.C = m->cfg.num_classes;
-    p.probs = a.probs;
-    p.logits = a.logits;
-    const size_t smem = gru_smem_bytes(p.in_dim);
-    long blocks = ntiles < sm_count() ? ntiles : sm_count();
-    if (last) {
-      KWS_CUDA_OK(cudaFuncSetAttribute(gru_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-      gru_layer_kernel<true><<<static_cast<unsigned>(blocks), kGruThreads, smem, st>>>(p);
-    } else {
-      KWS_CUDA_OK(cudaFuncSetAttribute(gru_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-      gru_layer_kernel<false><<<static_cast<unsigned>(blocks), kGruThreads, smem, st>>>(p);
-    }
-    KWS_LAUNCH_OK("gru_layer_kernel");
+    const int rc = launch_layer_fp32(m, a, l, l > 0 ? seq + ((l - 1) & 1) * per_buf : nullptr, last ? nullptr : seq + (l & 1) * per_buf, nullptr,
+                                     last, st);
+    if (rc != KWS_OK) return rc;
   }
   return KWS_OK;
 }

@@ -195,6 +195,7 @@ static void free_stream(kws_stream* st) {
   cudaFree(st->nframes);
   cudaFree(st->mel);
   cudaFree(st->seq);
+  cudaFree(st->y_rows);
   cudaFree(st->probs);
   cudaFree(st->tok);
   cudaFree(st->slot_frames);
@@ -253,6 +254,7 @@ extern "C" int kws_stream_create(kws_model* m, const kws_stream_config* cfg, kws
   if (rc == KWS_OK) rc = dev_alloc(&st->win_n, S, true);
   if (rc == KWS_OK) rc = dev_alloc(&st->trigger, S, true);
   if (rc == KWS_OK && mf > 0 && L > 1) rc = dev_alloc(&st->seq, seq_scratch_elems(st->S, mf, L), false);
+  if (rc == KWS_OK && mf > 0 && m->octbit) rc = dev_alloc(&st->y_rows, S * mf * kHidden, false);
   if (rc != KWS_OK) {
     free_stream(st);
     return rc;
@@ -378,6 +380,7 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
     a.x = st->mel;
     a.x_tiled = tiled;
     a.seq_scratch = st->seq;
+    a.y_rows_scratch = st->y_rows;
     a.S = S;
     a.n = n_step;
     a.seq_len = st->nframes;

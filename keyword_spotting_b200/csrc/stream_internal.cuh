@@ -20,6 +20,7 @@ struct kws_stream {
   int32_t* nframes = nullptr;       // [S]
   float* mel = nullptr;             // [S, max_frames, M]
   float* seq = nullptr;             // inter-layer hand-off, private so that stream objects can run concurrently
+  float* y_rows = nullptr;          // octbit graph only: [S, max_frames, H] last-layer outputs for the FC
   float* probs = nullptr;           // [S, max_frames, C]
   signed char* tok = nullptr;       // [S, W, fpad]
   unsigned char* slot_frames = nullptr;  // [S, W]

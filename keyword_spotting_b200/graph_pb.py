@@ -262,6 +262,7 @@ class OctbitNode:
     scale: float
     bias: np.ndarray              # [out] float32
     x_input: str
+    weight_name: str = ""         # name of the qint8 Const (the variable the MatMul read before the rewrite)
 
 
 def octbit_nodes(nodes: List[Node]) -> List[OctbitNode]:
@@ -292,5 +293,42 @@ def octbit_nodes(nodes: List[Node]) -> List[OctbitNode]:
         bias = n.attrs.get("bias")
         if not isinstance(scale, float) or not isinstance(bias, np.ndarray):
             raise GraphFormatError("OctbitMatMul %s: scale / bias attrs missing" % n.name)
-        out.append(OctbitNode(n.name, np.ascontiguousarray(wq), float(scale), bias.astype(np.float32).reshape(-1), n.inputs[0]))
+        out.append(OctbitNode(n.name, np.ascontiguousarray(wq), float(scale), bias.astype(np.float32).reshape(-1), n.inputs[0],
+                              w.name))
     return out
+
+
+def rnn_ctc_octbit_weights(nodes: List[Node], n_mel: Optional[int] = None, scope: str = "model"):
+    """Octbit-rewritten rnn_ctc deployment graph (``graph_octbit.pb``, main.py:357-371) ->
+    ``(ModelWeights, OctbitModelWeights)``.
+
+    The float Consts that survive the rewrite (cell_0, every bias, the mel basis, and the FC when it was left float)
+    are read as in ``rnn_ctc_weights``; every ``OctbitMatMul`` is mapped through the name of its qint8 Const
+    (``.../cell_{l}/gru_cell/{gates,candidate}/{kernel,weights}`` or ``.../weightsClasses``).  The float kernels of
+    converted MatMuls no longer exist in the graph; ``ModelWeights`` carries their dequantised image
+    (``W_q^T * scale``) so that the container stays complete -- the octbit forward never reads it."""
+    from .rnn_ctc import ModelWeights, OctbitMatrix, OctbitModelWeights
+    octs = octbit_nodes(nodes)
+    if not octs:
+        raise GraphFormatError("no OctbitMatMul node: not an octbit-rewritten graph")
+    ow = OctbitModelWeights()
+    deq: Dict[str, np.ndarray] = {}
+    for o in octs:
+        mat = OctbitMatrix(o.weight_q, float(np.float32(o.scale)), o.bias)
+        m = _CELL.search(o.weight_name)
+        if m and m.group(3) in ("kernel", "weights"):
+            (ow.gates if m.group(2) == "gates" else ow.candidate)[int(m.group(1))] = mat
+        elif o.weight_name.endswith("/weightsClasses"):
+            ow.fc = mat
+        else:
+            raise GraphFormatError("OctbitMatMul %s reads %s, which is not a GRU kernel or the FC of rnn_ctc" % (o.name, o.weight_name))
+        deq[o.weight_name] = (o.weight_q.T.astype(np.float32) * np.float32(o.scale)).astype(np.float32)
+    patched = []
+    for n in nodes:
+        if n.op == "Const" and n.name in deq:
+            n2 = Node(name=n.name, op=n.op, inputs=list(n.inputs), attrs=dict(n.attrs))
+            n2.attrs["value"] = deq[n.name]
+            patched.append(n2)
+        else:
+            patched.append(n)
+    return rnn_ctc_weights(patched, n_mel=n_mel, scope=scope), ow

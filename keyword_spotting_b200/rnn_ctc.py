@@ -106,6 +106,44 @@ class ModelWeights:
             raise _lib.InvalidArgumentError("fc_w/fc_b must be [%d,%d]/[%d]" % (H, C, C))
 
 
+@dataclass
+class OctbitMatrix:
+    """One converted MatMul of the octbit graph: qint8 Const ``[out, in]`` + the op's ``scale`` / ``bias`` attrs
+    (octbit/octbit_graph.py:191-215, 527-536)."""
+    weight_q: np.ndarray
+    scale: float
+    bias: np.ndarray
+
+
+@dataclass
+class OctbitModelWeights:
+    """The OctbitMatMul constants of ``graph_octbit.pb``: GRU layers by index (the rewriter converts every layer but
+    cell_0, octbit/octbit_graph.py:218-225) and the FC."""
+    gates: dict = field(default_factory=dict)        # layer -> OctbitMatrix [2H, in+H]
+    candidate: dict = field(default_factory=dict)    # layer -> OctbitMatrix [H, in+H]
+    fc: Optional[OctbitMatrix] = None                # [C, H]
+
+    @classmethod
+    def from_float(cls, weights: "ModelWeights", layers=None, fc: bool = True, device=None):
+        """What the reference's GraphRewriter produces from the float graph: ``octize_weight_int8_signed`` on the
+        kernels of every layer but the first (or ``layers``) and on the FC."""
+        from .octbit.octbit_graph import octize_weight_int8_signed
+        L = len(weights.gates_kernel)
+        layers = list(range(1, L)) if layers is None else list(layers)
+
+        def octize(w):
+            wq, scale, bias = octize_weight_int8_signed(np.ascontiguousarray(w, np.float32), device=device)
+            return OctbitMatrix(np.ascontiguousarray(wq, np.int8), float(np.float32(scale)), np.ascontiguousarray(bias, np.float32))
+
+        ow = cls()
+        for l in layers:
+            ow.gates[l] = octize(weights.gates_kernel[l])
+            ow.candidate[l] = octize(weights.cand_kernel[l])
+        if fc:
+            ow.fc = octize(weights.fc_w)
+        return ow
+
+
 class DeployModel:
     """models/rnn_ctc.py:113-166 on a B200.  Owns a ``kws_model`` handle."""
 
@@ -138,7 +176,56 @@ class DeployModel:
         _lib.check(self._lib.kws_model_create(ctypes.byref(cfg), ctypes.byref(cw), self.device.index,
                                               ctypes.byref(handle)))
         self._handle = handle
+        self.octbit = None
+        self._keep_oct = None
         self.set_precision(precision)
+
+    @classmethod
+    def from_octbit_graph(cls, path_or_bytes, config: Optional[Config] = None, device=None, n_mel: Optional[int] = None):
+        """The reference's deployable artefact ``graph_octbit.pb`` (main.py:357-371): float cell_0 + OctbitMatMul
+        everywhere else, read without TensorFlow and run through the octbit kernels."""
+        from . import graph_pb
+        weights, octw = graph_pb.rnn_ctc_octbit_weights(graph_pb.load_graph(path_or_bytes), n_mel=n_mel)
+        cfg = config or Config(n_mel=weights.mel_basis.shape[1], num_layers=len(weights.gates_kernel))
+        model = cls(cfg, weights, device=device, precision="fp32")
+        model.set_octbit(octw)
+        return model
+
+    def set_octbit(self, octw: Optional["OctbitModelWeights"]):
+        """Switch every forward of this model to the octbit-rewritten graph (``None``: back to the float graph).
+        Converted MatMuls use per-stream activation ranges, i.e. the reference's batch-1 semantics."""
+        if octw is None:
+            _lib.check(self._lib.kws_model_set_octbit(self._handle, None))
+            self.octbit = None
+            self._keep_oct = None
+            return
+        cw = _lib.OctbitWeights()
+        keep = []
+
+        def put(mat, rows, cols, what):
+            wq = np.ascontiguousarray(mat.weight_q, np.int8)
+            ob = np.ascontiguousarray(mat.bias, np.float32).reshape(-1)
+            if wq.shape != (rows, cols) or ob.shape != (rows,):
+                raise _lib.InvalidArgumentError("%s: weight_q must be [%d, %d] int8 and bias [%d], got %r / %r"
+                                                % (what, rows, cols, rows, wq.shape, ob.shape))
+            keep.extend([wq, ob])
+            return wq.ctypes.data_as(ctypes.c_void_p).value, float(mat.scale), ob.ctypes.data_as(ctypes.c_void_p).value
+
+        H, C, L = self.config.hidden_size, self.config.num_classes, self.config.num_layers
+        if set(octw.gates) != set(octw.candidate):
+            raise _lib.InvalidArgumentError("gates and candidate must be converted for the same layers")
+        for l in octw.gates:
+            if not 0 <= l < L:
+                raise _lib.InvalidArgumentError("layer %r out of range" % (l,))
+            K = (self.config.n_mel if l == 0 else H) + H
+            cw.gates_wq[l], cw.gates_scale[l], cw.gates_obias[l] = put(octw.gates[l], 2 * H, K, "gates[%d]" % l)
+            cw.cand_wq[l], cw.cand_scale[l], cw.cand_obias[l] = put(octw.candidate[l], H, K, "candidate[%d]" % l)
+        if octw.fc is not None:
+            cw.fc_wq, cw.fc_scale, cw.fc_obias = put(octw.fc, C, H, "fc")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.kws_model_set_octbit(self._handle, ctypes.byref(cw)))
+        self.octbit = octw
+        self._keep_oct = keep
 
     def set_precision(self, precision: str):
         modes = {"tc": _lib.PRECISION_TC_FP16, "fp32": _lib.PRECISION_FP32}

@@ -306,3 +306,99 @@ def deploy_forward(pcm: np.ndarray, state: np.ndarray, w: Weights, dtype=np.floa
 def pcm16_to_float(x: np.ndarray) -> np.ndarray:
     """detector.py:40-43 ``buf_to_float`` -- int16 LE PCM -> float32 * 2^-15."""
     return (np.float32(1.0 / 32768.0) * np.asarray(x, dtype=np.int16).astype(np.float32)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# the octbit-rewritten deployment graph (graph_octbit.pb: main.py:357-371,
+# octbit/octbit_graph.py:218-225, 461-536).  Every MatMul outside cell_0 is an
+# OctbitMatMul: gates / candidate of the upper layers and the FC.  The op
+# quantises with the min / max of the whole tensor it is called with
+# (octbit_mat_mul_op.cc:90-124); the reference deploys at batch 1, so every
+# stream below is its own sequence of op calls: [1, in+H] per step for the two
+# GRU MatMuls, [n, H] per chunk for the FC (inference2 flattens the frames).
+# --------------------------------------------------------------------------
+def octize_model(w: Weights, layers=None, fc=True):
+    """What GraphRewriter does to the float graph: ``{"gates": {l: (wq, scale, bias)}, "candidate": {...}, "fc": ...}``
+    with ``octize_weight_int8_signed`` (octbit_graph.py:191-215); ``scale`` rounded to the fp32 attr."""
+    from . import octbit as ooct
+    layers = list(range(1, w.num_layers)) if layers is None else list(layers)
+
+    def one(k):
+        wq, scale, bias = ooct.octize_weight_int8_signed(k)
+        return wq, float(np.float32(scale)), bias.astype(np.float32)
+
+    out = {"gates": {}, "candidate": {}, "fc": None}
+    for l in layers:
+        out["gates"][l] = one(w.gates_kernel[l])
+        out["candidate"][l] = one(w.cand_kernel[l])
+    if fc:
+        out["fc"] = one(w.fc_w)
+    return out
+
+
+def _octbit_op(x, mat, use_ref=True):
+    """One OctbitMatMul call: the unmodified reference kernel (oracle/_ref) when built, else the numpy restatement."""
+    from . import cref, octbit as ooct
+    wq, scale, bias = mat
+    x = np.ascontiguousarray(x, np.float32)
+    if use_ref and cref.have_ref():
+        return cref.ref_octbit_matmul(x, wq, bias, scale)
+    return ooct.octbit_mat_mul(x, wq, scale=np.float32(scale), bias=bias)
+
+
+def octbit_mel_forward(mel, state, w: Weights, octw, seq_len=None, use_ref=True, trace=None):
+    """(mel frames, rnn_state) -> (softmax, rnn_state, logits) of the octbit graph, stream by stream as the
+    reference runs it (batch 1).  ``trace``: optional dict filled with the inputs / raw outputs of every op call
+    of stream 0 (for op-level checks)."""
+    f32 = np.float32
+    mel = np.asarray(mel, f32)
+    S, n, _ = mel.shape
+    L, H, C = w.num_layers, w.hidden, w.num_classes
+    new_state = np.array(state, dtype=f32, copy=True)
+    probs = np.zeros((S, n, C), f32)
+    logits = np.zeros((S, n, C), f32)
+    for s in range(S):
+        length = n if seq_len is None else int(seq_len[s])
+        h = [new_state[l, s].copy() for l in range(L)]
+        ys = np.zeros((n, H), f32)
+        for t in range(n):
+            inp = mel[s, t]
+            live = t < length
+            for l in range(L):
+                if l in octw["gates"]:
+                    xh = np.concatenate([inp, h[l]])[None, :]
+                    g = _octbit_op(xh, octw["gates"][l], use_ref)[0]
+                    gates = _sigmoid((g + w.gates_bias[l]).astype(f32)).astype(f32)
+                    r, u = gates[:H], gates[H:]
+                    xrh = np.concatenate([inp, (r * h[l]).astype(f32)])[None, :]
+                    cpre = _octbit_op(xrh, octw["candidate"][l], use_ref)[0]
+                    c = np.tanh((cpre + w.cand_bias[l]).astype(f32)).astype(f32)
+                    nh = (u * h[l] + (f32(1) - u) * c).astype(f32)
+                    if trace is not None and s == 0:
+                        trace.setdefault("steps", []).append(dict(layer=l, t=t, xh=xh[0].copy(), g=g.copy(), xrh=xrh[0].copy(), c=cpre.copy()))
+                else:
+                    nh = gru_cell(inp[None, :], h[l][None, :], w.gates_kernel[l], w.gates_bias[l], w.cand_kernel[l],
+                                  w.cand_bias[l], f32)[0]
+                if live:
+                    h[l] = nh
+                inp = nh
+            ys[t] = inp if live else 0
+        if octw["fc"] is not None:
+            if length > 0:
+                lg = _octbit_op(ys[:length], octw["fc"], use_ref)
+                logits[s, :length] = (lg + w.fc_b).astype(f32)
+            logits[s, length:] = w.fc_b                      # zero rows: q = offset -> (sum - bias) = 0 -> logits = b
+        else:
+            logits[s] = (ys @ w.fc_w.astype(f32) + w.fc_b).astype(f32)
+        probs[s] = softmax(logits[s][None])[0]
+        for l in range(L):
+            new_state[l, s] = h[l]
+    return probs, new_state, logits
+
+
+def octbit_deploy_forward(pcm, state, w: Weights, octw, use_ref=True):
+    pcm = np.asarray(pcm)
+    if pcm.ndim == 1:
+        pcm = pcm[None, :]
+    mel = pcm_to_mel(pcm.astype(np.float32), w, np.float32)
+    return octbit_mel_forward(mel, state, w, octw, None, use_ref)

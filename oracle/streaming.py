@@ -74,7 +74,9 @@ class StreamOracle:
 
     def __init__(self, weights: om.Weights, n_streams: int, dtype=np.float32,
                  vad_rule="int", vad_thres=VAD_THRESHOLD, window=WINDOW_CHUNKS,
-                 label=KEYWORD, decode_thres=0.4):
+                 label=KEYWORD, decode_thres=0.4, forward=None):
+        # forward(pcm_f32 [S, L], state) -> (softmax, state, logits); default: the float deployment graph
+        self.forward = forward
         self.w = weights
         self.S = n_streams
         self.dtype = dtype
@@ -112,7 +114,10 @@ class StreamOracle:
         full = np.concatenate([self.res, data], axis=1)
         keep = residual_length(full.shape[1])
         self.res = full[:, -keep:]
-        softmax, state, _ = om.deploy_forward(full, self.state, self.w, self.dtype)
+        if self.forward is not None:
+            softmax, state, _ = self.forward(full, self.state)
+        else:
+            softmax, state, _ = om.deploy_forward(full, self.state, self.w, self.dtype)
         self.state = state
         trigger = np.zeros(self.S, dtype=np.int32)
         labels = []

@@ -61,6 +61,7 @@ static void free_model(kws_model* m) {
   if (!m) return;
   cudaFree(m->mel_basis);
   cudaFree(m->mel.quads);
+  free_frontend_tc_tables(m);
   cudaFree(m->twiddle400);
   for (int l = 0; l < kMaxLayers; ++l) {
     cudaFree(m->layer[l].gates_kernel);
@@ -129,6 +130,7 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
     kws::build_mel_quads(w->mel_basis, M, &quads, &m->mel.quads_per_warp);
     if (rc == KWS_OK) rc = upload(&m->mel.quads, quads.data(), quads.size());
   }
+  if (rc == KWS_OK) rc = build_frontend_tc_tables(m, w->mel_basis);
   std::vector<float2> tw(20 * 52);          // periodic k2-major table of W400^(n1*k2) (fft400.cuh: kTwStride = 52)
   for (int k2 = 0; k2 < 20; ++k2)
     for (int j = 0; j < 52; ++j) {

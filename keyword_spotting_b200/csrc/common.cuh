@@ -84,6 +84,14 @@ struct MelSparse {               // non-zero part of the mel basis as per-warp l
   int quads_per_warp = 0;
 };
 
+struct FrontendTcTables {        // tensor-core front end (frontend_tc.cu)
+  bool ready = false;
+  uint32_t* tw = nullptr;        // twiddles as TMEM rows [2 tiles][2 parts][128][40]
+  void* mel_seg = nullptr;       // int4 [n_mel]: {first bin, bins, offset into mel_w, 0}
+  float* mel_w = nullptr;        // the bands' non-zero spans, concatenated, zero-padded to multiples of 8 bins
+  int mel_nw = 0;
+};
+
 }  // namespace kws
 
 struct kws_model {
@@ -92,6 +100,7 @@ struct kws_model {
   int precision = KWS_PRECISION_TC_FP16;
   float* mel_basis = nullptr;     // [201, M] dense, as given
   kws::MelSparse mel;
+  kws::FrontendTcTables fe_tc;
   float2* twiddle400 = nullptr;   // [20*52] periodic k2-major twiddles (fft400.cuh kTwStride)
   kws::LayerWeights layer[kws::kMaxLayers];
   float* fc_w = nullptr;          // [H, C]
@@ -135,7 +144,13 @@ struct FrontendPre {
   unsigned char* silence = nullptr;   // [S]
   int32_t* nframes_out = nullptr;     // [S]
 };
-bool frontend_can_fuse_pre(int chunk_len, int tail_cap);
+bool frontend_can_fuse_pre(const kws_model* m, int chunk_len, int tail_cap);
+int build_frontend_tc_tables(kws_model* m, const float* basis /*[201, M] host*/);
+void free_frontend_tc_tables(kws_model* m);
+bool frontend_uses_tc(const kws_model* m, int pcm_dtype);
+int frontend_tc_item_frames();
+int launch_frontend_tc(const kws_model* m, const PcmSource& src, int64_t S, int32_t max_frames, const int32_t* nframes,
+                       float* mel_out, cudaStream_t st, const FrontendPre* pre, bool tiled_out);
 void build_mel_quads(const float* basis /*[201, M] host*/, int M, std::vector<MelQuad>* quads, int* quads_per_warp);
 // Stream-tiled mel scratch (front end -> tensor-core GRU): float4 chunk c (of Q = M/4) of frame t of stream s sits at
 // float4 index ((s/128 * n + t) * Q + c) * 128 + s % 128, so the 128 threads of a GRU tile read, and the front end

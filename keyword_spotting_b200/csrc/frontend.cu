@@ -436,7 +436,10 @@ static size_t frontend_smem_bytes(const kws_model* m) {
          sizeof(int) * 16 + (quads_in_smem(m) ? sizeof(MelQuad) * kFeWarps * m->mel.quads_per_warp : 0);
 }
 
-bool frontend_can_fuse_pre(int chunk_len, int tail_cap) {
+bool frontend_can_fuse_pre(const kws_model* m, int chunk_len, int tail_cap) {
+  // the whole [tail | chunk] must fit one work item: 32 frames / 5360 samples here, 30 frames (<= 5199 samples) on
+  // the tensor-core kernel
+  if (frontend_uses_tc(m, KWS_PCM_I16)) return chunk_len + tail_cap - 1 <= kFft + kHop * (frontend_tc_item_frames() - 1) + kHop - 1;
   return chunk_len + tail_cap - 1 <= kFeWinSamples;
 }
 
@@ -444,6 +447,7 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
                     const int32_t* nframes, float* mel_out, cudaStream_t st, const FrontendPre* pre, bool tiled_out) {
   if (S <= 0) return KWS_OK;
   if (max_frames <= 0 && !pre) return KWS_OK;
+  if (frontend_uses_tc(m, src.body_dtype)) return launch_frontend_tc(m, src, S, max_frames, nframes, mel_out, st, pre, tiled_out);
   FrontendParams p;
   p.src = src;
   p.S = S;

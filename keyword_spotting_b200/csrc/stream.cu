@@ -345,7 +345,7 @@ extern "C" int kws_stream_step(kws_stream* st, const int16_t* pcm, int32_t chunk
   src.head = st->tail[cur];
   src.ld_head = kTailCap;
   src.head_len = st->tail_len[cur];
-  const bool fused = frontend_can_fuse_pre(chunk_len, kTailCap);
+  const bool fused = frontend_can_fuse_pre(m, chunk_len, kTailCap);
   const bool tiled = mel_can_tile(m);
   cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (g_step_timing_on) {

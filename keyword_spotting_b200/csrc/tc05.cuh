@@ -83,6 +83,10 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
          | (static_cast<uint32_t>(M >> 4) << 24);  // m_dim
 }
 
+// same, B operand MN-major (N contiguous: 8 n-elements per 16-byte row, 8 k-rows per core matrix; in the smem
+// descriptor SBO is then the stride between 8-groups of N and LBO the stride between 8-groups of K)
+__host__ __device__ constexpr uint32_t idesc_f16_bmn(int M, int N) { return idesc_f16(M, N) | (1u << 16); }
+
 // ---- MMA (issued by ONE thread).  D[tmem] (+)= A[tmem] * B[smem]^T
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
   asm volatile(
@@ -130,6 +134,12 @@ __device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -163,6 +173,13 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 __host__ __device__ constexpr size_t canon_offset(int n, int k, int K) {
   return static_cast<size_t>(n / 8) * (static_cast<size_t>(K / 8) * 128) + static_cast<size_t>(k / 8) * 128 +
          static_cast<size_t>(n % 8) * 16 + static_cast<size_t>(k % 8) * 2;
+}
+
+// byte offset of element (n, k) of a [N, K] fp16 matrix in the canonical MN-major SWIZZLE_NONE layout
+// (LBO = 128 between 8-groups of K, SBO = (K/8)*128 between 8-groups of N)
+__host__ __device__ constexpr size_t canon_offset_mn(int n, int k, int K) {
+  return static_cast<size_t>(n / 8) * (static_cast<size_t>(K / 8) * 128) + static_cast<size_t>(k / 8) * 128 +
+         static_cast<size_t>(k % 8) * 16 + static_cast<size_t>(n % 8) * 2;
 }
 
 }  // namespace tc

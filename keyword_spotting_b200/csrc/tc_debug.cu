@@ -55,7 +55,7 @@ tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bpac
   __syncthreads();
   if (tid == 0) {
     tc::fence_after_sync();
-    const uint32_t idesc = tc::idesc_f16(128, N);
+    const uint32_t idesc = ss_mode == 2 ? tc::idesc_f16_bmn(128, N) : tc::idesc_f16(128, N);   // 2: B is MN-major
     const uint32_t sbo = static_cast<uint32_t>(K / 8) * 128;
     for (int k16 = 0; k16 < K / 16; ++k16) {
       const uint64_t bdesc = tc::smem_desc(tc::smem_u32(sB) + k16 * 256, 128, sbo);
@@ -85,6 +85,7 @@ tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bpac
 
 }  // namespace kws
 
+// ss_mode: 0 = A in TMEM, 1 = A in shared memory, 2 = A in shared memory and B in the MN-major layout.
 // A [128, K] fp32 (rounded to fp16 on the device), B [N, K] fp32 (rounded and packed on the host side of
 // this call) -> D [128, N] fp32 = A * B^T with fp32 accumulation.  N % 16 == 0, N <= 256, K % 32 == 0, K <= 256.
 extern "C" int kws_debug_tc_gemm(const float* A, const float* B_host, float* D, int N, int K, int ss_mode,
@@ -98,7 +99,7 @@ extern "C" int kws_debug_tc_gemm(const float* A, const float* B_host, float* D, 
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
       const __half h = __float2half_rn(B_host[static_cast<size_t>(n) * K + k]);
-      *reinterpret_cast<__half*>(&packed[tc::canon_offset(n, k, K)]) = h;
+      *reinterpret_cast<__half*>(&packed[ss_mode == 2 ? tc::canon_offset_mn(n, k, K) : tc::canon_offset(n, k, K)]) = h;
     }
   __half* dB = nullptr;
   KWS_CUDA_OK(cudaMalloc(&dB, packed.size()));

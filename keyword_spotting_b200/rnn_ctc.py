@@ -286,7 +286,7 @@ class DeployModel:
         st_out = torch.empty_like(st_in)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.kws_deploy_forward(
-                self._handle, _tensors.ptr(x), _lib.PCM_I16 if is_i16 else _lib.PCM_F32, S, Lsig, x.stride(0),
+                self._handle, _tensors.ptr(x), _lib.PCM_I16 if is_i16 else _lib.PCM_F32, S, Lsig, x.stride(0) if S > 1 else Lsig,
                 _tensors.ptr(st_in), _tensors.ptr(probs), _tensors.ptr(st_out), _tensors.ptr(logits),
                 _tensors.stream_ptr(self.device)))
         outs = [probs, st_out] + ([logits] if want_logits else [])
@@ -310,7 +310,8 @@ class DeployModel:
         mel = torch.empty((S, n, self.config.n_mel), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.kws_frontend_mel(self._handle, _tensors.ptr(x), _lib.PCM_I16 if is_i16 else _lib.PCM_F32,
-                                                  S, Lsig, x.stride(0), _tensors.ptr(mel), _tensors.stream_ptr(self.device)))
+                                                  S, Lsig, x.stride(0) if S > 1 else Lsig, _tensors.ptr(mel),
+                                                  _tensors.stream_ptr(self.device)))
         if host:
             torch.cuda.current_stream(self.device).synchronize()
             return _tensors.to_host(mel)

@@ -70,6 +70,8 @@ def parse_args():
     ap.add_argument("--no-ops", action="store_true", help="skip the `ops` block (configs 2/4/5 + custom ops, N=1 only)")
     ap.add_argument("--no-parity", action="store_true", help="skip the `parity_check` block")
     ap.add_argument("--no-graphs", action="store_true", help="e2e: enqueue copies and kernels directly instead of graph replay")
+    ap.add_argument("--frontend", default="fft", choices=["fft", "tc"],
+                    help="front-end formulation: fft = packed-real FFT on the CUDA cores (default), tc = hop-block DFTs on tcgen05")
     ap.add_argument("--fc-gain", type=float, default=3.0, help="scale of the random-init FC layer (see the docstring)")
     ap.add_argument("--keyword", default="1", help="keyword of the trigger test (reference default '1233')")
     ap.add_argument("--parity-streams", type=int, default=256)
@@ -448,6 +450,16 @@ def ops_block(args, torch, device, peaks):
     cfg = Config(n_mel=40)
     wts = ModelWeights.random_init(cfg, seed=1234)
     dm = DeployModel(cfg, wts, device=device)
+    # ---- the two front-end formulations side by side: 131,072 streams x one steady-state chunk (5120 samples, 30 frames)
+    pcm_fe = (torch.randn((131072, 5120), device=device, generator=g) * 800).clamp_(-32768, 32767).to(torch.int16)
+    fe = {}
+    for name in ("fft", "tc"):
+        dm.set_frontend(name)
+        fe[name + "_ms"] = timeit(lambda: dm.frontend(pcm_fe), iters=5)
+    dm.set_frontend("fft")
+    fe["workload"] = "kws_frontend_mel, 131072 x 5120 int16 samples -> [131072, 30, 40] mel (row-major, no fused pre-step)"
+    out["frontend_fft_vs_tc"] = fe
+    del pcm_fe
     S2 = 4096
     pcm16 = (torch.randn((S2, 48000), device=device, generator=g) * 800).clamp_(-32768, 32767).to(torch.int16)
     st0 = torch.zeros((2, S2, 128), device=device)
@@ -538,7 +550,7 @@ def run_ours(args, rank, world, local_rank):
     host_binding = sharding.bind_host_to_gpu(local_rank) if not args.no_bind else {"bound": False, "why": "--no-bind"}
     cfg = Config(n_mel=40)
     weights = boosted_weights(cfg, args.fc_gain)
-    model = DeployModel(cfg, weights, device=device, precision=args.precision)
+    model = DeployModel(cfg, weights, device=device, precision=args.precision, frontend=args.frontend)
     S = args.streams
     det = StreamingDetector(model, S, keyword=args.keyword)
     n_buf = 4 if S <= 262144 else 2                  # 4 x 1.26 GB of PCM >> 126 MB L2: every step reads HBM-cold input
@@ -632,7 +644,7 @@ def run_ours(args, rank, world, local_rank):
                           "exact fp32 FFMA kernel measured against the tensor-pipe peak; ") +
                          "algorithmic FLOP = 327,168 per frame (GRU 325,632 + FC 1,536), one launch per layer")
     fe_gbs = S * FE_BYTES_PER_STREAM_CHUNK / (fe_launch_ms * 1e-3) / 1e9
-    roof_fe = dict(kernel="frontend_kernel", bound="hbm", achieved=fe_gbs, peak=peaks["hbm"], unit="GB/s",
+    roof_fe = dict(kernel="frontend_kernel" if args.frontend == "fft" else "frontend_tc_kernel", bound="hbm", achieved=fe_gbs, peak=peaks["hbm"], unit="GB/s",
                    frac=fe_gbs / peaks["hbm"], traffic=traffic.get("frontend_kernel"), launch_ms=fe_launch_ms,
                    algorithmic_bytes=S * FE_BYTES_PER_STREAM_CHUNK, traffic_source=traffic.get("_source"),
                    peak_source=peaks["source"] + ", copy bandwidth",

@@ -88,8 +88,19 @@ typedef enum kws_precision {
   KWS_PRECISION_TC_FP16 = 1
 } kws_precision;
 
+/* Formulation of the front end (K1).  Both produce the same mel frames (parity tests run on both).
+ *   KWS_FRONTEND_FFT (default): packed-real 20x20 FFT on the CUDA cores / shared memory (csrc/frontend.cu).
+ *   KWS_FRONTEND_TC: hop-block partial DFTs on tcgen05 with the twiddles in tensor memory (csrc/frontend_tc.cu);
+ *     int16 PCM and n_mel <= 64 only -- other inputs run on the FFT kernel.  Same speed on B200, see DESIGN.md. */
+typedef enum kws_frontend {
+  KWS_FRONTEND_FFT = 0,
+  KWS_FRONTEND_TC = 1
+} kws_frontend;
+
 int kws_model_create(const kws_model_config* cfg, const kws_model_weights* host_weights,
                      int device, kws_model** out);
+int kws_model_set_frontend(kws_model* m, int frontend);
+int kws_model_get_frontend(const kws_model* m);
 int kws_model_destroy(kws_model* m);
 int kws_model_set_precision(kws_model* m, int precision);
 int kws_model_get_precision(const kws_model* m);

@@ -19,6 +19,9 @@ PCM_I16 = 1
 PRECISION_FP32 = 0
 PRECISION_TC_FP16 = 1
 
+FRONTEND_FFT = 0
+FRONTEND_TC = 1
+
 DECODE_CTC = 0
 DECODE_CTC2 = 1
 DECODE_STRICT = 2
@@ -84,6 +87,8 @@ _SIGNATURES = {
     "kws_model_destroy": (c_int, [c_void_p]),
     "kws_model_set_precision": (c_int, [c_void_p, c_int]),
     "kws_model_get_precision": (c_int, [c_void_p]),
+    "kws_model_set_frontend": (c_int, [c_void_p, c_int]),
+    "kws_model_get_frontend": (c_int, [c_void_p]),
     "kws_model_set_octbit": (c_int, [c_void_p, POINTER(OctbitWeights)]),
     "kws_model_is_octbit": (c_int, [c_void_p]),
     "kws_num_frames": (c_int, [c_void_p, c_int64]),

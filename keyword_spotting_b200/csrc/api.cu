@@ -122,6 +122,7 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
   kws_model* m = new kws_model();
   m->cfg = *cfg;
   m->device = device;
+  m->frontend = default_frontend();
   const int M = cfg->n_mel, H = kHidden, C = cfg->num_classes;
   int rc = upload(&m->mel_basis, w->mel_basis, static_cast<size_t>(kBins) * M);
   {
@@ -188,6 +189,16 @@ extern "C" int kws_model_set_precision(kws_model* m, int precision) {
 }
 
 extern "C" int kws_model_get_precision(const kws_model* m) { return m ? m->precision : -1; }
+
+extern "C" int kws_model_set_frontend(kws_model* m, int frontend) {
+  clear_error();
+  KWS_REQUIRE(m != nullptr, "model is NULL");
+  KWS_REQUIRE(frontend == KWS_FRONTEND_FFT || frontend == KWS_FRONTEND_TC, "unknown frontend %d", frontend);
+  m->frontend = frontend;
+  return KWS_OK;
+}
+
+extern "C" int kws_model_get_frontend(const kws_model* m) { return m ? m->frontend : -1; }
 
 namespace kws {
 int launch_gru(kws_model* m, const GruArgs& a, cudaStream_t st) {

@@ -98,6 +98,7 @@ struct kws_model {
   kws_model_config cfg;
   int device = 0;
   int precision = KWS_PRECISION_TC_FP16;
+  int frontend = KWS_FRONTEND_FFT;   // K1 formulation (kws_model_set_frontend)
   float* mel_basis = nullptr;     // [201, M] dense, as given
   kws::MelSparse mel;
   kws::FrontendTcTables fe_tc;
@@ -148,6 +149,7 @@ bool frontend_can_fuse_pre(const kws_model* m, int chunk_len, int tail_cap);
 int build_frontend_tc_tables(kws_model* m, const float* basis /*[201, M] host*/);
 void free_frontend_tc_tables(kws_model* m);
 bool frontend_uses_tc(const kws_model* m, int pcm_dtype);
+int default_frontend();           // KWS_FRONTEND=tc|fft in the environment, else fft
 int frontend_tc_item_frames();
 int launch_frontend_tc(const kws_model* m, const PcmSource& src, int64_t S, int32_t max_frames, const int32_t* nframes,
                        float* mel_out, cudaStream_t st, const FrontendPre* pre, bool tiled_out);

@@ -58,10 +58,14 @@ constexpr int kFtLoadWarp0 = 17, kFtLoadThreads = 7 * 32;      // the int16 -> f
 constexpr int kFtOutWarp0 = 24, kFtOutWarps = 8, kFtOutThreads = 32 * kFtOutWarps;   // the mel pass is latency-bound: 2 warps per scheduler
 constexpr int kFtThreads = 32 * 32;
 constexpr uint32_t kFtColA = 0;               // twiddles: [tile][part] x 40 columns (tile 0 cos, 1 -sin; part 0 hi, 1 lo)
-constexpr uint32_t kFtColD = 160;             // D_re: 128 columns, D_im: 128 columns
+// D_re: columns 160..287, D_im: 288..415.  One buffer: TMEM cannot hold two, and splitting an item's transforms into
+// two N halves that are released separately was measured SLOWER -- a tcgen05.mma of this shape occupies the issue
+// slot ~60 cycles whatever its N (64, 80 or 128), so 60 small MMAs cost twice what 30 big ones do.
+constexpr uint32_t kFtColD = 160;
 constexpr int kFtOutStride = 65;              // floats per frame row of the output tile (odd: conflict-free band writes)
 
-enum { kFbBfull0 = 0, kFbBfull1, kFbBempty0, kFbBempty1, kFbDfull, kFbDempty, kFbMagFull0, kFbMagFull1, kFbMagEmpty0, kFbMagEmpty1, kFbNum };
+enum { kFbBfull0 = 0, kFbBfull1, kFbBempty0, kFbBempty1, kFbDfull, kFbDempty, kFbMagFull0, kFbMagFull1, kFbMagEmpty0,
+       kFbMagEmpty1, kFbNum };
 
 struct FrontendTcParams {
   PcmSource src;
@@ -84,17 +88,15 @@ struct FrontendTcParams {
   int* len_next;
   unsigned char* silence;
   int* nframes_out;
-  volatile int* dbg;        // optional host-mapped progress markers (KWS_FT_DEBUG=1): survives a trapped kernel
+  volatile int* dbg;        // optional host-mapped timeline buffer (KWS_FT_DEBUG=1)
 };
 
-#define FT_MARK(slot, value)                                       \
-  do {                                                             \
-    if (p.dbg && lane == 0 && blockIdx.x == 0) {                   \
-      p.dbg[slot] = (value);                                       \
-      __threadfence_system();                                      \
-    }                                                              \
+// timeline (KWS_FT_DEBUG): low 32 bits of clock64 at key hand-overs of items 40..43 of CTA 0
+#define FT_TIME(role, ev)                                                                  \
+  do {                                                                                     \
+    if (p.dbg && lane == 0 && blockIdx.x == 0 && i >= 40 && i < 44)                        \
+      p.dbg[(static_cast<int>(i) - 40) * 64 + (role) * 8 + (ev)] = static_cast<int>(clock64()); \
   } while (0)
-
 __device__ __forceinline__ void ft_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
@@ -212,38 +214,52 @@ frontend_tc_kernel(const FrontendTcParams p) {
   if (warp == kFtMmaWarp) {
     // ================================================================ MMA issuer
     const bool lead = lane == 0;
-    const uint32_t idesc1 = tc::idesc_f16(128, 128);
     const uint64_t b1desc = tc::smem_desc(tc::smem_u32(sB1), kFtB1Lbo, kFtB1Sbo);
-    auto gemm1 = [&](long i) {
-      const int buf = static_cast<int>(i & 1);
-      FT_MARK(0, 100 + static_cast<int>(i) * 10);
-      ft_spin(&bars[kFbBfull0 + buf], static_cast<uint32_t>((i >> 1) & 1));
-      FT_MARK(0, 101 + static_cast<int>(i) * 10);
-      if (i > 0) ft_spin(&bars[kFbDempty], static_cast<uint32_t>((i - 1) & 1));
-      tc::fence_after_sync();
-      const uint64_t bS = b1desc + static_cast<uint64_t>((buf * 2 + 0) * (kFtB1Part >> 4));
-      const uint64_t bU = b1desc + static_cast<uint64_t>((buf * 2 + 1) * (kFtB1Part >> 4));
-#pragma unroll 1
+    // an item's block transforms: Re tile, then Im tile.  The issuing warp shares its scheduler with seven others and
+    // a tcgen05.mma holds the issue slot ~60 cycles: fully unrolled, every operand address in uniform registers.
+    const uint32_t idesc = tc::idesc_f16(128, 128);
+    auto gemm1 = [&](uint64_t bH, uint64_t bL) {
+#pragma unroll
       for (int tile = 0; tile < 2; ++tile) {
         const uint32_t d = tmem + kFtColD + 128 * tile;
         const uint32_t a_hi = tmem + kFtColA + 40 * (2 * tile), a_lo = a_hi + 40;
-#pragma unroll 1
+#pragma unroll
         for (int k16 = 0; k16 < kFtBlk / 16; ++k16) {
           const uint64_t step = static_cast<uint64_t>(k16 * ((2 * kFtB1Lbo) >> 4));
           if (lead) {
-            tc::mma_ts(d, a_hi + 8 * k16, bS + step, idesc1, k16 > 0);
-            tc::mma_ts(d, a_hi + 8 * k16, bU + step, idesc1, true);
-            tc::mma_ts(d, a_lo + 8 * k16, bS + step, idesc1, true);
+            tc::mma_ts(d, a_hi + 8 * k16, bH + step, idesc, k16 > 0);
+            tc::mma_ts(d, a_hi + 8 * k16, bL + step, idesc, true);
+            tc::mma_ts(d, a_lo + 8 * k16, bH + step, idesc, true);
           }
         }
       }
-      if (lead) {
-        tc::commit(&bars[kFbDfull]);
-        tc::commit(&bars[kFbBempty0 + buf]);
-      }
-      FT_MARK(0, 102 + static_cast<int>(i) * 10);
     };
-    for (long i = 0; i < n_mine; ++i) gemm1(i);     // item i+1's block transforms run under item i's combination
+    for (long i = 0; i < n_mine; ++i) {
+      const int buf = static_cast<int>(i & 1);
+      FT_TIME(0, 5);
+      ft_spin(&bars[kFbBfull0 + buf], static_cast<uint32_t>((i >> 1) & 1));
+      FT_TIME(0, 0);
+      if (i > 0) ft_spin(&bars[kFbDempty], static_cast<uint32_t>((i - 1) & 1));
+      tc::fence_after_sync();
+      FT_TIME(0, 1);
+      // (the buffer index is loop-carried, which the compiler cannot prove warp-uniform: branch on it so that every
+      // descriptor inside is derived from kernel constants and stays in uniform registers -- no per-MMA broadcast loop)
+      constexpr uint64_t kPart = static_cast<uint64_t>(kFtB1Part >> 4);
+      if (buf == 0) {
+        gemm1(b1desc, b1desc + kPart);
+        if (lead) {
+          tc::commit(&bars[kFbDfull]);
+          tc::commit(&bars[kFbBempty0]);
+        }
+      } else {
+        gemm1(b1desc + 2 * kPart, b1desc + 3 * kPart);
+        if (lead) {
+          tc::commit(&bars[kFbDfull]);
+          tc::commit(&bars[kFbBempty1]);
+        }
+      }
+      FT_TIME(0, 2);
+    }
   } else if (warp >= kFtLoadWarp0 && warp < kFtOutWarp0) {
     // ================================================================ PCM loaders: int16 -> (x_hi, x_lo) fp16 operands
     const int ltid = tid - 32 * kFtLoadWarp0;
@@ -263,7 +279,7 @@ frontend_tc_kernel(const FrontendTcParams p) {
       const int start = total_len - keep;
       int16_t* tnext = p.fuse_pre ? p.tail_next + s * 400 : nullptr;
       const bool tail_fast = p.fuse_pre && ((start | keep) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.tail_next) & 15) == 0;
-      if (warp == kFtLoadWarp0) FT_MARK(1, 200 + static_cast<int>(i) * 10);
+      if (warp == kFtLoadWarp0) FT_TIME(3, 0);
       const int n_pieces = p.fuse_pre ? kFtPieces + 10 : kFtPieces;       // the fused chunk may reach 5199 samples
       // every piece this thread owns is requested before anything is waited for: one HBM latency per item, not seven
       constexpr int kRounds = (kFtPieces + 10 + kFtLoadThreads - 1) / kFtLoadThreads;
@@ -276,7 +292,7 @@ frontend_tc_kernel(const FrontendTcParams p) {
         if (pc < n_pieces && fast && q + 8 <= total_len)
           pre[rd] = __ldg(reinterpret_cast<const uint4*>((q < head_len ? head : body) + q));
       }
-      if (i >= 2) tc::mbar_wait(&bars[kFbBempty0 + buf], static_cast<uint32_t>(((i >> 1) + 1) & 1));
+      if (i >= 2) ft_wait_hint(&bars[kFbBempty0 + buf], static_cast<uint32_t>(((i >> 1) + 1) & 1), 200);
       unsigned char* dstS = sB1 + (buf * 2 + 0) * kFtB1Part;
       unsigned char* dstU = sB1 + (buf * 2 + 1) * kFtB1Part;
       float vadf = 0.0f;
@@ -361,7 +377,7 @@ frontend_tc_kernel(const FrontendTcParams p) {
       }
       tc::fence_proxy_async();
       ft_arrive(&bars[kFbBfull0 + buf]);
-      if (warp == kFtLoadWarp0) FT_MARK(1, 201 + static_cast<int>(i) * 10);
+      if (warp == kFtLoadWarp0) FT_TIME(3, 1);
     }
   } else if (warp >= kFtOutWarp0) {
     // ================================================================ mel projection + output: lane = frame
@@ -380,9 +396,7 @@ frontend_tc_kernel(const FrontendTcParams p) {
       const int f0 = g * kFtFrames;
       int nfi = nfr - f0;
       nfi = nfi < 0 ? 0 : (nfi > kFtFrames ? kFtFrames : nfi);
-      if (warp == kFtOutWarp0) FT_MARK(3, 400 + static_cast<int>(i) * 10);
-      tc::mbar_wait(&bars[kFbMagFull0 + buf], static_cast<uint32_t>((i >> 1) & 1));
-      if (warp == kFtOutWarp0) FT_MARK(3, 401 + static_cast<int>(i) * 10);
+      ft_wait_hint(&bars[kFbMagFull0 + buf], static_cast<uint32_t>((i >> 1) & 1), 200);
       // bands q, q+8, ...: eight bins per trip (spans are zero-padded to multiples of 8): the eight magnitude loads
       // (32 consecutive floats each) and the two broadcast weight loads are independent, four accumulators
       const float* mcol = sMag + buf * kFtMagFloats + lane;
@@ -457,30 +471,40 @@ frontend_tc_kernel(const FrontendTcParams p) {
     const uint32_t dre = tmem + lane_sel + kFtColD + 32 * F, dim = dre + 128;
 
     for (long i = 0; i < n_mine; ++i) {
-      if (warp == 0) FT_MARK(2, 300 + static_cast<int>(i) * 10);
-      ft_wait_hint(&bars[kFbDfull], static_cast<uint32_t>(i & 1), 64);
+      if (warp == 0 || warp == 4 || warp == 8 || warp == 15) FT_TIME(warp == 0 ? 4 : (warp == 15 ? 5 : warp >> 2), 0);
+      ft_wait_hint(&bars[kFbDfull], static_cast<uint32_t>(i & 1), 100);
       tc::fence_after_sync();
-      if (warp == 0) FT_MARK(2, 301 + static_cast<int>(i) * 10);
+      if (warp == 0 || warp == 4 || warp == 8 || warp == 15) FT_TIME(warp == 0 ? 4 : (warp == 15 ? 5 : warp >> 2), 1);
       float2 mg[8];                                   // (|X_f(k)|, |X_f(200-k)|) of frames 8F .. 8F+7
+      // TMEM reads run at ~64 B/clk per SM and are what this role is bound by: every column is read exactly once.
+      // frames 8F+4sub .. +3 use blocks 16F+8sub .. +10 (two columns per block: x, (-1)^m x):
+      //   sub 0: columns 0..23 of the warp's window (blocks 0..11);  sub 1: keeps blocks 8..11, reads columns 24..39
+      uint32_t re[24], im[24];
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
-        // frames 8F+4sub .. +3 use blocks 16F+8sub .. +10: columns 32F+16sub .. +21 of D_re and D_im
-        uint32_t re[24], im[24];
-        {
+        if (sub == 0) {
           uint32_t a16[16], a8[8], b16[16], b8[8];
-          tc::ld16(dre + 16 * sub, a16);
-          tc::ld8(dre + 16 * sub + 16, a8);
-          tc::ld16(dim + 16 * sub, b16);
-          tc::ld8(dim + 16 * sub + 16, b8);
+          tc::ld16(dre, a16);
+          tc::ld8(dre + 16, a8);
+          tc::ld16(dim, b16);
+          tc::ld8(dim + 16, b8);
           tc::wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) { re[j] = a16[j]; im[j] = b16[j]; }
 #pragma unroll
           for (int j = 0; j < 8; ++j) { re[16 + j] = a8[j]; im[16 + j] = b8[j]; }
-        }
-        if (sub == 1) {                               // every TMEM read of this item is done: D may be overwritten
-          tc::fence_before_sync();
+        } else {
+          uint32_t a16[16], b16[16];
+          tc::ld16(dre + 24, a16);
+          tc::ld16(dim + 24, b16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { re[j] = re[16 + j]; im[j] = im[16 + j]; }
+          tc::wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { re[8 + j] = a16[j]; im[8 + j] = b16[j]; }
+          tc::fence_before_sync();                    // every TMEM read of this item is done: the half may be overwritten
           ft_arrive(&bars[kFbDempty]);
+          if (warp == 0 || warp == 4 || warp == 8 || warp == 15) FT_TIME(warp == 0 ? 4 : (warp == 15 ? 5 : warp >> 2), 2);
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -504,7 +528,7 @@ frontend_tc_kernel(const FrontendTcParams p) {
         }
       }
       const int mbuf = static_cast<int>(i & 1);
-      if (i >= 2) tc::mbar_wait(&bars[kFbMagEmpty0 + mbuf], static_cast<uint32_t>(((i >> 1) + 1) & 1));
+      if (i >= 2) ft_wait_hint(&bars[kFbMagEmpty0 + mbuf], static_cast<uint32_t>(((i >> 1) + 1) & 1), 200);
       if (k <= 100) {                                 // lanes 101..127 carry zero twiddle rows (nothing to store)
         float* dk = mag_k + mbuf * kFtMagFloats;
         *reinterpret_cast<float4*>(dk) = make_float4(mg[0].x, mg[1].x, mg[2].x, mg[3].x);
@@ -516,10 +540,9 @@ frontend_tc_kernel(const FrontendTcParams p) {
         }
       }
       ft_arrive(&bars[kFbMagFull0 + mbuf]);
-      if (warp == 0) FT_MARK(2, 302 + static_cast<int>(i) * 10);
+      if (warp == 0 || warp == 4 || warp == 8 || warp == 15) FT_TIME(warp == 0 ? 4 : (warp == 15 ? 5 : warp >> 2), 3);
     }
   }
-  FT_MARK(4 + (warp >> 2), 999);
   tc::fence_before_sync();
   __syncthreads();
   if (warp == kFtMmaWarp) tc::tmem_dealloc(tmem, 512);
@@ -583,15 +606,20 @@ void free_frontend_tc_tables(kws_model* m) {
   m->fe_tc = FrontendTcTables();
 }
 
-// Which front end serves this launch: the tensor-core kernel for int16 PCM (the production path), the FFT kernel for
-// float PCM (arbitrary floats have no exact two-term fp16 split) and for filterbanks wider than 64 bands.
-// KWS_FRONTEND=fft in the environment forces the FFT kernel (A/B measurements).
+// Which front end serves this launch.  The FFT kernel (frontend.cu) is the default: on B200 the two run at the same
+// speed (2.4 ms for 131,072 x 30 frames) and the FFT is the more accurate one (1e-7 vs 3e-7 of the float64 spectrum).
+// The tensor-core kernel is selected per model (kws_model_set_frontend) or with KWS_FRONTEND=tc in the environment; it
+// serves int16 PCM only (arbitrary floats have no exact two-term fp16 split) and filterbanks of up to 64 bands.
 bool frontend_uses_tc(const kws_model* m, int pcm_dtype) {
-  static const bool force_fft = [] {
+  return m->frontend == KWS_FRONTEND_TC && m->fe_tc.ready && pcm_dtype == KWS_PCM_I16;
+}
+
+int default_frontend() {
+  static const int choice = [] {
     const char* e = std::getenv("KWS_FRONTEND");
-    return e && e[0] == 'f';
+    return e && e[0] == 't' ? KWS_FRONTEND_TC : KWS_FRONTEND_FFT;
   }();
-  return m->fe_tc.ready && pcm_dtype == KWS_PCM_I16 && !force_fft;
+  return choice;
 }
 
 int frontend_tc_item_frames() { return kFtFrames; }
@@ -637,11 +665,11 @@ int launch_frontend_tc(const kws_model* m, const PcmSource& src, int64_t S, int3
   if (dbg_on) {
     if (!dbg_host) {
       int* h = nullptr;
-      KWS_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&h), 64 * sizeof(int), cudaHostAllocMapped));
+      KWS_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&h), 256 * sizeof(int), cudaHostAllocMapped));
       KWS_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dbg_dev), h, 0));
       dbg_host = h;
     }
-    for (int i = 0; i < 64; ++i) dbg_host[i] = 0;
+    for (int i = 0; i < 256; ++i) dbg_host[i] = 0;
     p.dbg = dbg_dev;
   }
   const size_t smem = frontend_tc_smem_bytes(p.mel_nw);
@@ -652,8 +680,22 @@ int launch_frontend_tc(const kws_model* m, const PcmSource& src, int64_t S, int3
   if (dbg_on) {
     const cudaError_t e = cudaStreamSynchronize(st);
     fprintf(stderr, "[frontend_tc] S=%ld groups=%d sync=%s markers:", static_cast<long>(S), p.groups, cudaGetErrorString(e));
-    for (int i = 0; i < 60; ++i) fprintf(stderr, i >= 20 && i < 40 ? " %08x" : " %d", dbg_host[i]);
     fprintf(stderr, "\n");
+    if (dbg_host[1]) {
+      const unsigned t0 = static_cast<unsigned>(dbg_host[0]);
+      const char* roles[6] = {"mma : got_Bfull got_Dempty issued | (5) poll_Bfull", "epi warp 4: wait_Dfull got_Dfull arrive_Dempty mags_out",
+                              "epi warp 8: wait_Dfull got_Dfull arrive_Dempty mags_out", "load: start arrive_Bfull",
+                              "epi warp 0: wait_Dfull got_Dfull arrive_Dempty mags_out", "epi warp 15: wait_Dfull got_Dfull arrive_Dempty mags_out"};
+      for (int it = 0; it < 4; ++it)
+        for (int r = 0; r < 6; ++r) {
+          fprintf(stderr, "[frontend_tc] item %d %s:", 40 + it, roles[r]);
+          for (int e = 0; e < 6; ++e) {
+            const int v = dbg_host[it * 64 + r * 8 + e];
+            if (v) fprintf(stderr, " %u", static_cast<unsigned>(v) - t0);
+          }
+          fprintf(stderr, "\n");
+        }
+    }
   }
   KWS_LAUNCH_OK("frontend_tc_kernel");
   return KWS_OK;

@@ -148,9 +148,10 @@ class DeployModel:
     """models/rnn_ctc.py:113-166 on a B200.  Owns a ``kws_model`` handle."""
 
     def __init__(self, config: Optional[Config] = None, weights: Optional[ModelWeights] = None, device=None,
-                 precision: str = "tc"):
+                 precision: str = "tc", frontend: Optional[str] = None):
         """``precision``: ``"tc"`` (default) = tcgen05 tensor cores, fp16 operands / fp32 accumulate and state;
-        ``"fp32"`` = every product in fp32 on the CUDA cores (the accuracy baseline)."""
+        ``"fp32"`` = every product in fp32 on the CUDA cores (the accuracy baseline).
+        ``frontend``: ``"fft"`` (default) or ``"tc"`` (hop-block DFTs on tcgen05; int16 PCM) -- same results, same speed."""
         self.config = config or Config()
         self.device = _tensors.require_cuda(device)
         self.weights = weights if weights is not None else ModelWeights.random_init(self.config)
@@ -179,6 +180,16 @@ class DeployModel:
         self.octbit = None
         self._keep_oct = None
         self.set_precision(precision)
+        if frontend is not None:
+            self.set_frontend(frontend)
+        self.frontend_kind = {_lib.FRONTEND_FFT: "fft", _lib.FRONTEND_TC: "tc"}[int(self._lib.kws_model_get_frontend(self._handle))]
+
+    def set_frontend(self, frontend: str):
+        modes = {"fft": _lib.FRONTEND_FFT, "tc": _lib.FRONTEND_TC}
+        if frontend not in modes:
+            raise _lib.InvalidArgumentError("frontend must be 'fft' or 'tc'")
+        _lib.check(self._lib.kws_model_set_frontend(self._handle, modes[frontend]))
+        self.frontend_kind = frontend
 
     @classmethod
     def from_octbit_graph(cls, path_or_bytes, config: Optional[Config] = None, device=None, n_mel: Optional[int] = None):

@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="recurrent kernel: tc = tcgen05 fp16 operands / fp32 accumulate (default), fp32 = exact FFMA path")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--waves", type=int, default=16, help="e2e: the streams of a GPU are served in this many waves "
+    ap.add_argument("--waves", type=int, default=32, help="e2e: the streams of a GPU are served in this many waves "
                     "(independent stream objects on their own CUDA streams) so copies overlap compute and a chunk's "
                     "latency is one wave's, not the whole batch's")
     ap.add_argument("--depth", type=int, default=2, help="e2e: waves in flight")

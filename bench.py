@@ -70,6 +70,10 @@ def parse_args():
     ap.add_argument("--no-ops", action="store_true", help="skip the `ops` block (configs 2/4/5 + custom ops, N=1 only)")
     ap.add_argument("--no-parity", action="store_true", help="skip the `parity_check` block")
     ap.add_argument("--no-graphs", action="store_true", help="e2e: enqueue copies and kernels directly instead of graph replay")
+    ap.add_argument("--workload", default="streaming", choices=["streaming", "attention"],
+                    help="streaming = BASELINE configs[2] (the headline, default); attention = configs[4]: attention_ctc, "
+                         "n_mel 60, batched 8 s utterances sharded by utterance over the GPUs (no collective)")
+    ap.add_argument("--utterances", type=int, default=512, help="--workload attention: 8 s utterances per GPU and step")
     ap.add_argument("--frontend", default="fft", choices=["fft", "tc"],
                     help="front-end formulation: fft = packed-real FFT on the CUDA cores (default), tc = hop-block DFTs on tcgen05")
     ap.add_argument("--fc-gain", type=float, default=3.0, help="scale of the random-init FC layer (see the docstring)")
@@ -771,6 +775,77 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_attention(args, rank, world, local_rank):
+    """BASELINE configs[4]: attention_ctc (n_mel 60, combine_frame 2, 3 x {8-head attention, FFN 512}) on batched 8 s
+    utterances, sharded by utterance across the GPUs with no collective.  One step = `--utterances` utterances per GPU:
+    int16 PCM -> mel (K1) -> positional encoding (K6) -> attention forward -> softmax [B, 400, 6]."""
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    from keyword_spotting_b200 import AttentionConfig, AttentionDeployModel, sharding
+    am = AttentionDeployModel(AttentionConfig(), device=device)
+    B, L = args.utterances, 128000
+    g = torch.Generator(device=device).manual_seed(4321 + rank)
+    pcm = [(torch.randn((B, L), device=device, generator=g) * 800).clamp_(-32768, 32767).to(torch.int16) for _ in range(2)]
+    host = [p_.cpu().pin_memory() for p_ in pcm]
+    stream = torch.cuda.current_stream(device)
+    out = [None]
+
+    def step_dev(i):
+        out[0] = am(pcm[i % 2])
+
+    staging = torch.empty_like(pcm[0])
+    probs_host = torch.empty((B, am.frames(am._frontend.num_frames(L)), 6), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        staging.copy_(host[i % 2], non_blocking=True)
+        probs_host.copy_(am(staging), non_blocking=True)
+
+    for i in range(max(args.warmup, 3)):
+        step_dev(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, _ = timed_loop(torch, step_dev, args.steps, stream, barrier)
+    total_ms = sharding.reduce_max_scalar(total_ms, device)
+    for i in range(2):
+        step_e2e(i)
+    e_ms, _ = timed_loop(torch, step_e2e, args.steps, stream, barrier)
+    e_ms = sharding.reduce_max_scalar(e_ms, device)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        audio = world * B * 8.0 * args.steps
+        Tp = int(probs_host.shape[1])
+        flop = B * (Tp * 120 * 128 * 2 + 3 * (Tp * 128 * 384 * 2 + 2 * 8 * Tp * Tp * 16 * 2 + 2 * Tp * 128 * 512 * 2) + Tp * 128 * 6 * 2)
+        peaks = load_peaks()
+        line = dict(metric="attention_ctc audio-sec/sec (BASELINE configs[4])", value=audio / (total_ms * 1e-3), unit=UNIT,
+                    n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=total_ms / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload="attention_ctc forward (BASELINE configs[4]): %d x 8 s utterances per GPU, n_mel 60, int16 PCM "
+                                         "resident in HBM -> mel -> PE -> 3 x {8-head attention, FFN 512} -> softmax [B, %d, 6]" % (B, Tp),
+                                utterances_per_gpu=B, sharding="utterances/dp%d" % world,
+                                l2_policy="inputs larger than L2: 2 rotating %.0f MB PCM buffers" % (B * L * 2 / 1e6)),
+                    utterances_per_s=world * B * args.steps / (total_ms * 1e-3),
+                    roofline=dict(kernel="att_linear_kernel + att_attention_kernel (fp32 FFMA)", bound="tensor",
+                                  achieved=flop * args.steps / (total_ms * 1e-3) / 1e12, peak=peaks["bf16"], unit="TFLOP/s",
+                                  frac=flop * args.steps / (total_ms * 1e-3) / 1e12 / peaks["bf16"], traffic=None,
+                                  note="0.69 GFLOP per utterance; the contractions run on the CUDA cores (fp32), see DESIGN.md"),
+                    e2e=dict(value=audio / (e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * L * 2, d2h_bytes_per_step=B * Tp * 6 * 4,
+                             ms_per_step=e_ms / args.steps,
+                             note="pinned host int16 PCM -> H2D -> AttentionDeployModel call -> D2H softmax, every step"),
+                    gpu_launches=26 * args.steps, clocks=clocks)
+        print(json.dumps(line), flush=True)
+    am.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -778,6 +853,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.workload == "attention":
+        run_attention(args, rank, world, local_rank)
         return
     run_ours(args, rank, world, local_rank)
 

@@ -8,7 +8,7 @@ from oracle import model as om
 from tests._util import synth_pcm16, to_product_weights
 
 ow = om.init_weights(seed=1234, n_mel=40)
-dm = DeployModel(Config(n_mel=40), to_product_weights(ow))
+dm = DeployModel(Config(n_mel=40), to_product_weights(ow), frontend="tc")
 rng = np.random.default_rng(5678)
 shapes = [(1, 400), (1, 5120), (3, 5120), (7, 559), (2, 48000), (300, 5120)]
 if len(sys.argv) > 1:

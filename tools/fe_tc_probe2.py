@@ -8,7 +8,7 @@ from oracle import model as om
 from tests._util import to_product_weights
 
 ow = om.init_weights(seed=1234, n_mel=40)
-dm = DeployModel(Config(n_mel=40), to_product_weights(ow))
+dm = DeployModel(Config(n_mel=40), to_product_weights(ow), frontend="tc")
 rng = np.random.default_rng(1)
 L = 48000
 t = np.arange(L) / 16000.0

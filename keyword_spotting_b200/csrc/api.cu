@@ -77,6 +77,7 @@ static void free_model(kws_model* m) {
   if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
   cudaFree(m->scratch_mel);
   cudaFree(m->scratch_seq);
+  cudaFree(m->tc_xt);
   free_octbit(m);
   delete m;
 }
@@ -148,8 +149,11 @@ extern "C" int kws_model_create(const kws_model_config* cfg, const kws_model_wei
     if (rc == KWS_OK) rc = upload(&m->layer[l].cand_bias, w->cand_bias[l], H);
     if (rc == KWS_OK) {
       std::vector<__half> packed;
-      pack_tc_weights(w->gates_kernel[l], w->cand_kernel[l], in, /*split=*/l == 0 && in <= 64, &packed, &m->layer[l].tc_kx,
-                      &m->layer[l].tc_kxw);
+      // the unbounded mel input is split into hi/lo fp16 operands when the wider weights still fit (gru_tc.cu)
+      const bool last = l == cfg->num_layers - 1;
+      const bool split = l == 0 && in <= 64 && gru_tc_can_split(in, last, device);
+      if (l == 0 && !gru_tc_layer_fits(in, split, last, device)) m->tc_fits = false;   // (very wide inputs) the model then runs the fp32 kernel
+      pack_tc_weights(w->gates_kernel[l], w->cand_kernel[l], in, split, &packed, &m->layer[l].tc_kx, &m->layer[l].tc_kxw);
       __half* dptr = nullptr;
       rc = upload(&dptr, packed.data(), packed.size());
       m->layer[l].tc_wpack = dptr;

@@ -117,6 +117,9 @@ struct kws_model {
   kws::OctbitMatrix oct_gates[kws::kMaxLayers], oct_cand[kws::kMaxLayers], oct_fc;
   float* oct_y_rows = nullptr;    // [S, n, H] last-layer outputs for the FC (non-stream forwards)
   size_t oct_y_cap = 0;
+  bool tc_fits = true;            // every layer fits the tensor-core recurrent kernel's shared memory (set at creation)
+  void* tc_xt = nullptr;          // row-tiled fp16 copy of a caller's row-major x (kws_gru_forward on the tensor-core path)
+  size_t tc_xt_bytes = 0;
   cudaStream_t aux_stream = nullptr;          // second stream + events of the layer pipeline for small batches (gru_tc.cu)
   std::vector<cudaEvent_t> aux_events;
 };
@@ -154,19 +157,26 @@ int frontend_tc_item_frames();
 int launch_frontend_tc(const kws_model* m, const PcmSource& src, int64_t S, int32_t max_frames, const int32_t* nframes,
                        float* mel_out, cudaStream_t st, const FrontendPre* pre, bool tiled_out);
 void build_mel_quads(const float* basis /*[201, M] host*/, int M, std::vector<MelQuad>* quads, int* quads_per_warp);
-// Stream-tiled mel scratch (front end -> tensor-core GRU): float4 chunk c (of Q = M/4) of frame t of stream s sits at
-// float4 index ((s/128 * n + t) * Q + c) * 128 + s % 128, so the 128 threads of a GRU tile read, and the front end
-// writes, 16-byte pieces that are contiguous across streams.  Size: ceil(S/128)*128 * n * M floats.
+// Stream-tiled mel scratch (front end -> tensor-core GRU, tc05.cuh "row-tiled A operand"): the fp16 MMA operand of
+// layer 0, [S/128 tiles][n frames][x_hi chunks | x_lo chunks][128 streams][8 mels]; chunk c holds mels 8c..8c+7 (zero
+// past n_mel, up to kx = ceil16(n_mel)), x = x_hi + x_lo.  The front end writes 16-byte pieces that are contiguous
+// across streams, the recurrent kernel takes a whole tile-step (kxw/8 * 2048 bytes) with one bulk copy.
+// Size: ceil(S/128)*128 * n * 2*kx halves = ... * kx floats (also enough for the row-major fp32 mel of other paths).
 constexpr int kTcMaxClasses = 8;   // FC columns the tensor-core recurrent kernel keeps per thread (gru_tc.cu)
 // The tensor-core recurrent kernel serves models of up to kTcMaxClasses classes; wider FC layers run on the exact fp32
 // kernel whatever the requested precision (never a silently truncated softmax).
 inline bool model_uses_tc(const kws_model* m) {
-  return !m->octbit && m->precision == KWS_PRECISION_TC_FP16 && m->cfg.num_classes <= kTcMaxClasses;
+  return !m->octbit && m->precision == KWS_PRECISION_TC_FP16 && m->cfg.num_classes <= kTcMaxClasses && m->tc_fits;
 }
-inline bool mel_can_tile(const kws_model* m) { return model_uses_tc(m) && m->cfg.n_mel % 4 == 0; }
+inline bool mel_can_tile(const kws_model* m) { return model_uses_tc(m); }
 inline size_t mel_scratch_elems(int64_t S, int32_t n, int n_mel) {
-  return static_cast<size_t>(ceil_div(S, 128) * 128) * static_cast<size_t>(n > 0 ? n : 1) * n_mel;
+  return static_cast<size_t>(ceil_div(S, 128) * 128) * static_cast<size_t>(n > 0 ? n : 1) * ((n_mel + 15) / 16 * 16);
 }
+// layer-0 operand geometry of the tiled mel scratch: chunks of 8 mels per half, and whether the lo half exists
+inline int mel_tile_chunks(const kws_model* m) { return m->layer[0].tc_kx / 8; }
+inline bool mel_tile_split(const kws_model* m) { return m->layer[0].tc_kxw != m->layer[0].tc_kx; }
+bool gru_tc_can_split(int in_dim, bool last, int device);                // gru_tc.cu
+bool gru_tc_layer_fits(int in_dim, bool split, bool last, int device);
 int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t max_frames,
                     const int32_t* nframes /*[S] or null*/, float* mel_out, cudaStream_t st,
                     const FrontendPre* pre = nullptr, bool tiled_out = false);

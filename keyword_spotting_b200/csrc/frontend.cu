@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tc05.cuh"
 #include "fft400.cuh"
 
 namespace kws {
@@ -68,8 +69,11 @@ struct FrontendParams {
   const MelQuad* mel_q;     // [10 warps][quads_per_warp] (common.cuh)
   int mel_qpw;              // quads per warp (even)
   int vec_ok;               // int16 sources are 8-byte aligned with row strides % 4 == 0
-  float* mel_out;           // [S, max_frames, n_mel], or stream-tiled (common.cuh) when tiled_out
+  float* mel_out;           // [S, max_frames, n_mel], or the recurrent kernel's fp16 operand (common.cuh) when tiled_out
   int tiled_out;
+  int tile_chunks;          // tiled_out: chunks of 8 mels per half (kx / 8)
+  int tile_split;           // tiled_out: the lo half (what the fp16 rounding lost) follows the hi half
+  unsigned c_magic;         // ceil(2^32 / tile_chunks)
   unsigned q_magic;         // ceil(2^32 / (n_mel / 4)): i / Q == umulhi(i, q_magic) for i < 2^16
   float mag_scale;          // 0.5 * (int16 input ? 2^-15 : 1), applied to the finished band sums
   // fused server pre-step (only with groups == 1 and int16 input): VAD, frame count, next tail
@@ -351,23 +355,34 @@ frontend_kernel(const FrontendParams p) {
       int nfi = nfr - f0;
       if (nfi > kFeItemFrames) nfi = kFeItemFrames;
       const int total = nfi > 0 ? nfi * M : 0;
-      if ((M & 3) == 0 && (p.tiled_out || (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0)) {
-        // 16-byte pieces: chunk c (of Q) of frame f goes to row-major (s*n + f0 + f)*Q + c or, stream-tiled, to
-        // ((tile*n + f0 + f)*Q + c)*128 + stream%128
-        const int Q = M >> 2;
-        float4* dst4 = reinterpret_cast<float4*>(p.mel_out);
-        long step = 1;
-        if (p.tiled_out) {
-          dst4 += ((s >> 7) * p.max_frames + f0) * static_cast<long>(Q) * 128 + (s & 127);
-          step = 128;
-        } else {
-          dst4 += (s * p.max_frames + f0) * static_cast<long>(Q);
+      if (p.tiled_out) {
+        // the recurrent kernel's layer-0 operand (common.cuh): per frame, chunks of 8 mels as fp16 and (split) chunks of
+        // what that rounding lost; the 16-byte piece (frame, chunk) of stream s sits between those of its 127 tile mates
+        const int nc = p.tile_chunks;
+        const int per_frame = p.tile_split ? 2 * nc : nc;
+        uint4* dst = reinterpret_cast<uint4*>(p.mel_out) + ((s >> 7) * p.max_frames + f0) * static_cast<long>(per_frame) * 128 + (s & 127);
+        const int pieces = nfi > 0 ? nfi * nc : 0;
+        for (int i = tid; i < pieces; i += kFeThreads) {
+          const int f = nc == 1 ? i : static_cast<int>(__umulhi(static_cast<unsigned>(i), p.c_magic));   // i / nc, i < 2^16
+          const int c = i - f * nc;
+          const float* src = out_tile + f * Mp + 8 * c;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 8 * c + j < M ? src[j] : 0.0f;
+          uint4 hi, lo;
+          tc::split_half8(v, &hi, &lo);
+          dst[(f * per_frame + c) * 128] = hi;
+          if (p.tile_split) dst[(f * per_frame + nc + c) * 128] = lo;
         }
+      } else if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0) {
+        // 16-byte pieces: chunk c (of Q) of frame f goes to row-major (s*n + f0 + f)*Q + c
+        const int Q = M >> 2;
+        float4* dst4 = reinterpret_cast<float4*>(p.mel_out) + (s * p.max_frames + f0) * static_cast<long>(Q);
         for (int i = tid; i < (total >> 2); i += kFeThreads) {
           const int f = Q == 1 ? i : static_cast<int>(__umulhi(static_cast<unsigned>(i), p.q_magic));   // i / Q, i < 2^16
           const int c = i - f * Q;
           const float* src = out_tile + f * Mp + 4 * c;
-          dst4[i * step] = make_float4(src[0], src[1], src[2], src[3]);
+          dst4[i] = make_float4(src[0], src[1], src[2], src[3]);
         }
       } else {
         float* dst = p.mel_out + (s * p.max_frames + f0) * M;
@@ -463,7 +478,9 @@ int launch_frontend(const kws_model* m, const PcmSource& src, int64_t S, int32_t
   p.mel_out = mel_out;
   p.tiled_out = tiled_out ? 1 : 0;
   p.q_magic = m->cfg.n_mel >= 4 ? static_cast<unsigned>(((1ull << 32) + (m->cfg.n_mel / 4) - 1) / (m->cfg.n_mel / 4)) : 0u;
-  if (tiled_out && (m->cfg.n_mel & 3)) return fail(KWS_ERR_INVALID_ARGUMENT, "tiled mel output needs n_mel % 4 == 0");
+  p.tile_chunks = tiled_out ? mel_tile_chunks(m) : 1;
+  p.tile_split = tiled_out && mel_tile_split(m) ? 1 : 0;
+  p.c_magic = static_cast<unsigned>(((1ull << 32) + p.tile_chunks - 1) / p.tile_chunks);
   p.mag_scale = src.body_dtype == KWS_PCM_I16 ? 0.5f / 32768.0f : 0.5f;
   p.fuse_pre = 0;
   p.vad_limit = 0;

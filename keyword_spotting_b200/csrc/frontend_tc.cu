@@ -81,6 +81,9 @@ struct FrontendTcParams {
   int vec_ok;
   float* mel_out;
   int tiled_out;
+  int tile_chunks;          // tiled_out: chunks of 8 mels per half (kx / 8), whether the lo half follows, ceil(2^32 / chunks)
+  int tile_split;
+  unsigned c_magic;
   unsigned q_magic;
   int fuse_pre;
   long long vad_limit;
@@ -426,21 +429,32 @@ frontend_tc_kernel(const FrontendTcParams p) {
       ft_arrive(&bars[kFbMagEmpty0 + buf]);          // this thread's magnitude reads are done
       asm volatile("bar.sync 3, 256;" ::: "memory");
       const int total = nfi * M;
-      if ((M & 3) == 0 && (p.tiled_out || (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0)) {
-        const int Q = M >> 2;
-        float4* dst4 = reinterpret_cast<float4*>(p.mel_out);
-        long step = 1;
-        if (p.tiled_out) {
-          dst4 += ((s >> 7) * p.max_frames + f0) * static_cast<long>(Q) * 128 + (s & 127);
-          step = 128;
-        } else {
-          dst4 += (s * p.max_frames + f0) * static_cast<long>(Q);
+      if (p.tiled_out) {
+        // the recurrent kernel's layer-0 operand (common.cuh): fp16 hi chunks and, split, lo chunks of 8 mels
+        const int nc = p.tile_chunks;
+        const int per_frame = p.tile_split ? 2 * nc : nc;
+        uint4* dst = reinterpret_cast<uint4*>(p.mel_out) + ((s >> 7) * p.max_frames + f0) * static_cast<long>(per_frame) * 128 + (s & 127);
+        const int pieces = nfi > 0 ? nfi * nc : 0;
+        for (int idx = otid; idx < pieces; idx += kFtOutThreads) {
+          const int f = nc == 1 ? idx : static_cast<int>(__umulhi(static_cast<unsigned>(idx), p.c_magic));
+          const int c = idx - f * nc;
+          const float* src = sOut + f * kFtOutStride + 8 * c;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 8 * c + j < M ? src[j] : 0.0f;
+          uint4 hi, lo;
+          tc::split_half8(v, &hi, &lo);
+          dst[(f * per_frame + c) * 128] = hi;
+          if (p.tile_split) dst[(f * per_frame + nc + c) * 128] = lo;
         }
+      } else if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mel_out) & 15) == 0) {
+        const int Q = M >> 2;
+        float4* dst4 = reinterpret_cast<float4*>(p.mel_out) + (s * p.max_frames + f0) * static_cast<long>(Q);
         for (int idx = otid; idx < (total >> 2); idx += kFtOutThreads) {
           const int f = Q == 1 ? idx : static_cast<int>(__umulhi(static_cast<unsigned>(idx), p.q_magic));
           const int c = idx - f * Q;
           const float* src = sOut + f * kFtOutStride + 4 * c;
-          dst4[idx * step] = make_float4(src[0], src[1], src[2], src[3]);
+          dst4[idx] = make_float4(src[0], src[1], src[2], src[3]);
         }
       } else {
         float* dst = p.mel_out + (s * p.max_frames + f0) * M;
@@ -642,7 +656,9 @@ int launch_frontend_tc(const kws_model* m, const PcmSource& src, int64_t S, int3
   p.mel_out = mel_out;
   p.tiled_out = tiled_out ? 1 : 0;
   p.q_magic = m->cfg.n_mel >= 4 ? static_cast<unsigned>(((1ull << 32) + (m->cfg.n_mel / 4) - 1) / (m->cfg.n_mel / 4)) : 0u;
-  if (tiled_out && (m->cfg.n_mel & 3)) return fail(KWS_ERR_INVALID_ARGUMENT, "tiled mel output needs n_mel % 4 == 0");
+  p.tile_chunks = tiled_out ? mel_tile_chunks(m) : 1;
+  p.tile_split = tiled_out && mel_tile_split(m) ? 1 : 0;
+  p.c_magic = static_cast<unsigned>(((1ull << 32) + p.tile_chunks - 1) / p.tile_chunks);
   p.fuse_pre = 0;
   p.vad_limit = 0;
   p.tail_next = nullptr;

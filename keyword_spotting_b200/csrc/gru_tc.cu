@@ -7,35 +7,41 @@
 //   * one CTA owns 128 streams for a whole layer -- the streams are the M dimension of tcgen05.mma
 //     (M=128, cta_group::1); the TMEM lane of a stream is owned by the same thread for the whole chunk, so the
 //     fp32 master state h never leaves registers between time steps;
-//   * all weights of the layer ([384, K] fp16, 135-196 KB) are resident in shared memory for the whole
+//   * all weights of the layer ([384, K] fp16, 172-196 KB) are resident in shared memory for the whole
 //     kernel, in the K-major SWIZZLE_NONE canonical layout, packed on the host at model creation;
-//   * the A operand [x_t | h_{t-1}] (and [x_t | r*h]) lives in TENSOR MEMORY (TS-form MMA): each thread writes
-//     its own stream's row with tcgen05.st, so activations never touch shared memory and no proxy fence is
-//     needed.  TMEM map (512 columns): D_r 0..127, D_u 128..255, D_cand 256..383, A_x, A_h;
+//   * the recurrent A operand (h_{t-1}, then r*h) lives in TENSOR MEMORY (TS-form MMA): each thread writes its own
+//     stream's row with tcgen05.st, so the recurrent activations never touch shared memory;
+//   * the input A operand x_t never touches a thread at all: the producer of x (the front end for layer 0, the
+//     layer below otherwise) leaves it in HBM as fp16 in the row-tiled operand layout (tc05.cuh: [tile][t][K/8 chunks]
+//     [128 streams][8 elements]), so ONE bulk async copy (cp.async.bulk, completion on an mbarrier) per tile-step
+//     lands an MMA-ready SS-form operand in shared memory, double-buffered, a step ahead;
+//   * TMEM map (512 columns): D_r 0..127, D_u 128..255, D_cand 256..383, A_h 384..447;
 //   * the input projection is not a separate GEMM: x_t W[0:in] is accumulated into the same TMEM tile as
 //     h W[in:], and it is issued a phase early so it never sits on the recurrent critical path;
 //   * warp-specialised: warps 0-15 run the gate algebra from TMEM (warp w: the 32 streams of TMEM lane quarter w%4,
-//     hidden units [32*(w/4), +32) -- four warps per scheduler hide the MUFU / TMEM-load latencies); warp 16 only
-//     issues MMAs.  Everything is handed over with mbarriers (tcgen05.commit one way,
-//     512-thread arrivals the other) -- no CTA-wide barrier inside the time loop.  Per step:
-//         MMA warp                                   epilogue threads
-//         r-gate x-part             <- A_x ready     ...
-//         r-gate h-part -> commit R <- A_h ready
-//         u-gate x+h    -> commit U                  wait R: r = sigmoid(D_r), keep fp16(r*h) in registers
-//         cand  x-part                               wait U: A_h <- r*h, arrive;  D_u <- u = sigmoid(D_u) in place
-//         cand  h-part  -> commit C <- A_rh ready    wait C: A_x <- x_{t+1}, arrive (next r-gate x-part overlaps)
-//                                                    c = tanh(D_c), h' = c + u (h - c), FC partials, A_h <- h', arrive
+//     hidden units [32*(w/4), +32) -- four warps per scheduler hide the MUFU / TMEM-load latencies); warp 16 issues
+//     the bulk copies and the MMAs.  Everything is handed over with mbarriers (tcgen05.commit and copy completion one
+//     way, 512-thread arrivals the other) -- no CTA-wide barrier inside the time loop.  Per step:
+//         warp 16                                          gate threads
+//         r-gate h-part -> commit R      <- A_h ready      ...
+//         copy x_{t+1} -> other buffer
+//         u-gate x+h    -> commit U                        wait R: r = sigmoid(D_r), keep fp16(r*h) in registers
+//         cand  x-part                                     wait U: A_h <- r*h, arrive;  u = sigmoid(D_u) -> registers
+//         cand  h-part  -> commit C      <- A_rh ready     wait C: c = tanh(D_c), h' = c + u (h - c), A_h <- h', arrive
+//         r-gate x-part of step t+1      <- x_{t+1} landed FC partials / softmax / hand-off stores of step t
 //     so the dependent chain of a step is  r-MMA(h) -> sigmoid -> cand-MMA(h) -> tanh,  with the u gate, all
-//     x-part MMAs, the softmax and the global loads/stores running beside it;
+//     x-part MMAs, the copies, the softmax and the global stores running beside it;
 //   * gate algebra in fp32 with ex2.approx / rcp.approx and packed f32x2 arithmetic (FFMA2/FADD2/FMUL2); activations
-//     are evaluated four at a time sharing one reciprocal (5 MUFU per 4 activations, 3.75 per hidden unit and step --
-//     the MUFU pipe is what this kernel is bound by), biases pre-scaled by log2(e).
-// Operands are fp16 (weights rounded once on the host, activations rounded when written to TMEM), accumulation
+//     are evaluated four at a time sharing one reciprocal (5 MUFU per 4 activations, 3.75 per hidden unit and step),
+//     biases pre-scaled by log2(e).  Each accumulator column is read from TMEM exactly once per step (the TMEM read
+//     port moves 64 B/clk: a [128,128] fp32 gate costs 1024 cycles per read).
+// Operands are fp16 (weights rounded once on the host, activations rounded by their producer), accumulation
 // and all state fp32.  The layer-0 input projection is the exception: mel features are unbounded (tens for loud
 // audio) and a single fp16 rounding of x and W_x alone costs up to 3e-3 on the carried state, so that product is
 // issued as three fp16 MMAs  x_hi*W_hi + x_lo*W_hi + x_hi*W_lo  (x = x_hi + x_lo, W = W_hi + W_lo; the
-// dropped lo*lo term is 2^-22 relative), i.e. at fp32-grade accuracy for +6 small MMAs per step.  With it the
-// deviation from the fp32 graph stays below 1e-3 (contract) on probabilities and state; see DESIGN.md.
+// dropped lo*lo term is 2^-22 relative), i.e. at fp32-grade accuracy for +6 small MMAs per step: the front end
+// writes both halves of the split.  With it the deviation from the fp32 graph stays below 1e-3 (contract) on
+// probabilities and state; see DESIGN.md.
 #include <type_traits>
 #include <vector>
 
@@ -47,29 +53,26 @@ namespace kws {
 constexpr int kTcTile = 128;
 constexpr int kTcEpiWarps = 16;           // warps 0-15: gate algebra.  Warp w owns TMEM lanes 32*(w%4).. (its 32 streams)
 constexpr int kTcEpiThreads = 32 * kTcEpiWarps;   //   and the 32 hidden units [32*(w/4), +32) of those streams
-constexpr int kTcThreads = kTcEpiThreads + 128;   // + warpgroup 4: warp 16 issues the MMAs (warps 17-19 only donate registers)
+constexpr int kTcThreads = kTcEpiThreads + 128;   // + warpgroup 4: warp 16 issues the x copies and the MMAs (warps 17-19 only donate registers)
 constexpr int kTcUnits = 32;              // hidden units per gate thread
 
 
 struct GruTcParams {
   int kx;                      // x width padded to a multiple of 16
-  int kxw;                     // x columns of the packed weights: 2*kx when the x product is split (layer 0), else kx
-  int in_dim;                  // true x width
+  int kxw;                     // x columns of the operand and of the packed weights: 2*kx when the x product is split
+  int nbuf;                    // x buffers in shared memory: 2, or 1 when two do not fit
   long S;
   int n;                       // frames of the whole sequence: the time stride of x, the hand-off, probs and logits
   int t0, nt;                  // this launch runs frames [t0, t0 + nt) (the layers of long sequences are pipelined in time chunks)
-  const float* x_f32;          // layer 0: mel fp32, [S, n, in_dim] row-major or stream-tiled (x_tiled, see common.cuh)
-  int x_tiled;
-  const __half* x_f16;         // layer > 0: fp16, stream-tiled [tile][t][16 chunks][128 streams][8 units]
-  __half* y_f16;               // non-last layers: same tiled layout
+  const unsigned char* x_tiles;   // layer 0: fp16 row-tiled operand [tile][t][kxw/8 chunks][128 streams][8]: [x_hi | x_lo (split)]
+  const __half* x_f16;         // layers above: the layer below's outputs, same layout with 16 chunks
+  __half* y_f16;               // non-last layers: outputs in that layout
   const __half* wpack;         // [384, kxw+128] fp16, canonical layout: [Wx_hi | Wx_lo (split only) | Wh]
   const float* bias;           // [384] = gates (r | u) | candidate
   const float* h_in;           // [S, 128]
   float* h_out;                // [S, 128]
   const int* seq_len;
   const unsigned char* zero_state;
-  const float* fc_w;           // [128, C]
-  const float* fc_b;           // [C]
   int C;
   float* probs;                // [S, n, C]
   float* logits;               // [S, n, C] or null
@@ -170,21 +173,26 @@ __device__ __forceinline__ void mbar_acquire(uint64_t* bar, uint32_t parity) {
 __device__ long long g_tc_timeline[64 * 8];
 static int g_tc_timeline_on = 0;
 
-enum { kBarAX = 0, kBarAH, kBarARH, kBarR, kBarU, kBarC, kNumBars };
+enum { kBarXF0 = 0, kBarXF1, kBarAX, kBarXD, kBarAH, kBarARH, kBarR, kBarU, kBarC, kNumBars };
 
-// kFirst: layer 0 -- x is fp32 (mel) and its projection uses the 3-term split.
-// kFirst: layer 0 -- x is fp32 (mel) and its projection uses the 3-term split.
-template <bool kLast, bool kFirst>
+// kXSmem: the x operand arrives in shared memory by bulk copy (layer 0: 24 KB per tile-step next to 172 KB of weights).
+//   The layers above (32 KB per tile-step next to 196 KB of weights: no room) take x through the gate threads into
+//   TMEM columns 448..511 instead, loaded a step ahead.
+// kNX: k16 steps of the x operand when they are known at compile time, so that the issuing warp runs straight-line
+//   code -- 8: a 128-wide layer below (not split), 3: the 40-mel front end (split); 0: taken from the parameters.
+template <bool kLast, bool kXSmem, int kNX>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gru_tc_kernel(const GruTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int ktot = p.kxw + kHidden;                                                  // K extent of the packed weights
+  const uint32_t xbytes = static_cast<uint32_t>(p.kxw / 8) * tc::kTileChunkBytes;    // one tile-step of x
   unsigned char* sW = smem;                                                         // [384, ktot] fp16
-  float* sBias = reinterpret_cast<float*>(smem + static_cast<size_t>(384) * ktot * 2);   // [384] pre-scaled
-  float* sXch = sBias + 384;                                               // [3][128][8] FC partials of unit blocks 1..3
+  unsigned char* sX = sW + static_cast<size_t>(768) * ktot;                         // kXSmem: [nbuf][kxw/8 chunks][128][8] fp16
+  float* sBias = reinterpret_cast<float*>(sX + (kXSmem ? static_cast<size_t>(p.nbuf) * xbytes : 0));   // [384] pre-scaled
+  float* sXch = sBias + 384;                                               // [3][128][8] FC partials of unit blocks 1..3 (last layer)
   float* sFc = sXch + 3 * kTcTile * kTcMaxClasses;                         // [128][8] FC weights (last layer)
   float* sProb = sFc + kHidden * kTcMaxClasses;                            // [4 steps][6][128] parked probabilities (last layer)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sProb + (kLast ? 4 * 6 * kTcTile : 0));   // [kNumBars]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kLast ? sProb + 4 * 6 * kTcTile : sBias + 384);   // [kNumBars]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -192,7 +200,10 @@ gru_tc_kernel(const GruTcParams p) {
 
   if (warp == kMmaWarp) tc::tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
+    tc::mbar_init(&bars[kBarXF0], 1);               // the issuing lane's arrive.expect_tx + the copy's bytes
+    tc::mbar_init(&bars[kBarXF1], 1);
     tc::mbar_init(&bars[kBarAX], kTcEpiThreads);
+    tc::mbar_init(&bars[kBarXD], 1);
     tc::mbar_init(&bars[kBarAH], kTcEpiThreads);
     tc::mbar_init(&bars[kBarARH], kTcEpiThreads);
     tc::mbar_init(&bars[kBarR], 1);
@@ -215,64 +226,129 @@ gru_tc_kernel(const GruTcParams p) {
   tc::fence_after_sync();
 
   const uint32_t tmem = *tmem_slot;
-  const uint32_t colDr = 0, colDu = 128, colDc = 256, colAx = 384;
-  const uint32_t colAxl = colAx + p.kx / 2;                       // x_lo (split only)
-  const bool split = kFirst && p.kxw != p.kx;                     // 3-term x product (needs 2*kx/2 + 64 <= 128 columns)
-  const uint32_t colAh = colAx + p.kxw / 2;
+  const uint32_t colDr = 0, colDu = 128, colDc = 256, colAh = 384, colAx = 448;
   const long ntiles = (p.S + kTcTile - 1) / kTcTile;
+  const int t_end = p.t0 + p.nt;
 
   if (warp >= kMmaWarp) {
-    // =========================================================== MMA issuer (one elected lane of warp 16)
+    // =========================================================== x copies + MMA issue (one elected lane of warp 16)
+    // (setmaxnreg is a warpgroup-wide instruction: warps 16-19 must all execute the same one)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == kMmaWarp) {
-      const uint32_t sbo = static_cast<uint32_t>(ktot / 8) * 128;
-      const uint32_t idesc128 = tc::idesc_f16(128, 128);
-      const int nx = p.kx / 16, nxw = p.kxw / 16;
-      const bool lead = lane == 0;
-      // All operand addresses are computed warp-uniformly (they live in uniform registers); only the MMA itself is
-      // predicated on the elected lane.  B descriptor of K-chunk k16 for the weight rows starting at row0 =
-      // base + ((row0/8)*sbo + 256*k16)/16 added to the 14-bit start-address field (shared memory < 256 KB: no carry).
-      const uint64_t wbase = tc::smem_desc(tc::smem_u32(sW), 128, sbo);
-      const uint32_t row_step = (16 * sbo) >> 4;                             // 128 output rows
-      // x-part of a product into D columns `dcol` (overwrites D), weight rows starting at 128*rblk
-      auto issue_x = [&](uint32_t dcol, int rblk) {
-        const uint64_t wrow = wbase + rblk * row_step;
-#pragma unroll 1
-        for (int k16 = 0; k16 < nx; ++k16)                                   // x_hi * Wx_hi
-          if (lead) tc::mma_ts(tmem + dcol, tmem + colAx + 8 * k16, wrow + 16 * k16, idesc128, k16 > 0);
-        if (split) {
-#pragma unroll 1
-          for (int k16 = 0; k16 < nx; ++k16)                                 // x_lo * Wx_hi
-            if (lead) tc::mma_ts(tmem + dcol, tmem + colAxl + 8 * k16, wrow + 16 * k16, idesc128, true);
-#pragma unroll 1
-          for (int k16 = 0; k16 < nx; ++k16)                                 // x_hi * Wx_lo
-            if (lead) tc::mma_ts(tmem + dcol, tmem + colAx + 8 * k16, wrow + 16 * (nx + k16), idesc128, true);
-        }
-      };
-      auto issue_h = [&](uint32_t dcol, int rblk) {                          // += A_h * Wh[128*rblk .. +127]
-        const uint64_t wrow = wbase + rblk * row_step + 16 * nxw;
-#pragma unroll 1
-        for (int k16 = 0; k16 < kHidden / 16; ++k16)
-          if (lead) tc::mma_ts(tmem + dcol, tmem + colAh + 8 * k16, wrow + 16 * k16, idesc128, true);
-      };
-      uint32_t it = 0;
-      for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int t = 0; t < p.nt; ++t, ++it) {
-          const uint32_t par = it & 1;
-          mbar_acquire(&bars[kBarAX], par);
-          issue_x(colDr, 0);                                                 // r gate, x-part (D_r is free since the last r epilogue)
-          mbar_acquire(&bars[kBarAH], par);
-          issue_h(colDr, 0);
-          if (lead) tc::commit(&bars[kBarR]);
-          issue_x(colDu, 1);                                                 // u gate: D_u held the activated u until now
-          issue_h(colDu, 1);
-          if (lead) tc::commit(&bars[kBarU]);
-          issue_x(colDc, 2);                                                 // candidate, x-part
-          mbar_acquire(&bars[kBarARH], par);
-          issue_h(colDc, 2);
-          if (lead) tc::commit(&bars[kBarC]);
+    const bool lead = lane == 0;
+    const int nx = kNX ? kNX : p.kx / 16;
+    const bool split = kNX ? kNX == 3 : p.kxw != p.kx;             // 3-term x product
+    const bool two = p.nbuf == 2;
+    const uint32_t sbo = static_cast<uint32_t>(ktot / 8) * 128;
+    const uint32_t idesc128 = tc::idesc_f16(128, 128);
+    // All operand addresses are computed warp-uniformly (they live in uniform registers); only the MMA itself is
+    // predicated on the elected lane.  B descriptor of K-chunk k16 for the weight rows starting at row0 =
+    // base + ((row0/8)*sbo + 256*k16)/16 added to the 14-bit start-address field (shared memory < 256 KB: no carry).
+    const uint64_t wbase = tc::smem_desc(tc::smem_u32(sW), 128, sbo);
+    const uint32_t row_step = (16 * sbo) >> 4;                             // 128 output rows
+    const uint64_t xdesc0 = tc::smem_desc(tc::smem_u32(sX), tc::kTileChunkBytes, 128);   // A, row-tiled: LBO 2048 (K), SBO 128 (M)
+    const uint64_t xdesc1 = xdesc0 + (xbytes >> 4);
+    constexpr uint32_t kStepA = (2 * tc::kTileChunkBytes) >> 4;           // one k16 step of the A operand: two chunks
+    // The TMEM base comes out of shared memory, i.e. in a vector register the compiler cannot prove warp-uniform: every
+    // TMEM operand address derived from it would be hoisted out of the time loop as an invariant and, at 32 registers,
+    // spilled to local memory and reloaded per MMA.  `tm` is redefined (opaquely) at every step, so the addresses are
+    // recomputed next to their MMA instead: one add in the uniform datapath.
+    uint32_t tm = tmem;
+    uint64_t wb = wbase, xd0 = xdesc0, xd1 = xdesc1;       // (same for the descriptor bases: 64-bit invariants per gate and K step otherwise)
+    // x-part of a product into D columns `dcol` (overwrites D), weight rows starting at 128*rblk
+    auto issue_x_from = [&](uint64_t xdesc, uint32_t dcol, int rblk) {
+      const uint64_t wrow = wb + rblk * row_step;
+      const uint64_t xlo = xdesc + static_cast<uint64_t>(nx) * kStepA;    // the lo chunks follow the hi chunks
+#pragma unroll
+      for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                     // x_hi * Wx_hi
+        if (lead) tc::mma_ss(tm + dcol, xdesc + k16 * kStepA, wrow + 16 * k16, idesc128, k16 > 0);
+      if (split) {
+#pragma unroll
+        for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                   // x_lo * Wx_hi
+          if (lead) tc::mma_ss(tm + dcol, xlo + k16 * kStepA, wrow + 16 * k16, idesc128, true);
+#pragma unroll
+        for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                   // x_hi * Wx_lo
+          if (lead) tc::mma_ss(tm + dcol, xdesc + k16 * kStepA, wrow + 16 * (nx + k16), idesc128, true);
+      }
+    };
+    // (the buffer index is loop-carried, which the compiler cannot prove warp-uniform: branch on it so that every
+    // descriptor is derived from kernel constants and stays in uniform registers)
+    auto issue_x = [&](int buf, uint32_t dcol, int rblk) {
+      if (!kXSmem) {                                                       // x in TMEM (never split: a layer's outputs are in [-1, 1])
+        const uint64_t wrow = wb + rblk * row_step;
+#pragma unroll
+        for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)
+          if (lead) tc::mma_ts(tm + dcol, tm + colAx + 8 * k16, wrow + 16 * k16, idesc128, k16 > 0);
+      } else if (buf == 0) {
+        issue_x_from(xd0, dcol, rblk);
+      } else {
+        issue_x_from(xd1, dcol, rblk);
+      }
+    };
+    const int nxw = p.kxw / 16;
+    auto issue_h = [&](uint32_t dcol, int rblk) {                          // += A_h * Wh[128*rblk .. +127]
+      const uint64_t wrow = wb + rblk * row_step + 16 * nxw;
+#pragma unroll
+      for (int k16 = 0; k16 < kHidden / 16; ++k16)
+        if (lead) tc::mma_ts(tm + dcol, tm + colAh + 8 * k16, wrow + 16 * k16, idesc128, true);
+    };
+    auto prefetch = [&](long tile, int t, int buf) {                       // x of (tile, t) -> buffer `buf`
+      if (lead) {
+        tc::mbar_arrive_expect_tx(&bars[kBarXF0 + buf], xbytes);
+        tc::bulk_g2s(sX + static_cast<size_t>(buf) * xbytes, p.x_tiles + (tile * p.n + t) * static_cast<long>(xbytes), xbytes,
+                     &bars[kBarXF0 + buf]);
+      }
+    };
+    uint32_t it = 0;                                                       // (tile, step) pairs done by this CTA
+    if (static_cast<long>(blockIdx.x) < ntiles && p.nt > 0) {
+      if (kXSmem) {
+        prefetch(blockIdx.x, p.t0, 0);
+        mbar_acquire(&bars[kBarXF0], 0);
+      } else {
+        mbar_acquire(&bars[kBarAX], 0);
+      }
+      issue_x(0, colDr, 0);                                                // r gate, x-part of the very first step
+    }
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int t = p.t0; t < t_end; ++t, ++it) {
+        const uint32_t par = it & 1;
+        const int buf = two ? static_cast<int>(it & 1) : 0;
+        asm volatile("" : "+r"(tm), "+l"(wb), "+l"(xd0), "+l"(xd1));
+        const bool step_next = t + 1 < t_end;
+        const long ntile = step_next ? tile : tile + gridDim.x;            // what this CTA runs next
+        const int nt1 = step_next ? t + 1 : p.t0;
+        const bool has_next = ntile < ntiles;
+        mbar_acquire(&bars[kBarAH], par);                                  // h_{t-1} in A_h; every MMA of the previous step is complete
+        issue_h(colDr, 0);
+        if (lead) tc::commit(&bars[kBarR]);
+        if (kXSmem && two && has_next) prefetch(ntile, nt1, buf ^ 1);      // the other buffer's last readers were the previous step's MMAs
+        issue_x(buf, colDu, 1);                                            // u gate
+        issue_h(colDu, 1);
+        if (lead) tc::commit(&bars[kBarU]);
+        issue_x(buf, colDc, 2);                                            // candidate, x-part
+        if (!kXSmem && lead) tc::commit(&bars[kBarXD]);                    // A_x has been read: the gate threads may store x_{t+1}
+        mbar_acquire(&bars[kBarARH], par);                                 // r*h in A_h (and D_r read by every gate thread)
+        issue_h(colDc, 2);
+        if (lead) tc::commit(&bars[kBarC]);
+        if (has_next) {
+          if (kXSmem) {
+            int nb = buf ^ 1;
+            uint32_t xpar = ((it + 1) >> 1) & 1;
+            if (!two) {                                                    // one buffer: it is free once this step's MMAs are complete
+              mbar_acquire(&bars[kBarC], par);
+              prefetch(ntile, nt1, 0);
+              nb = 0;
+              xpar = (it + 1) & 1;
+            }
+            mbar_acquire(&bars[kBarXF0 + nb], xpar);
+            issue_x(nb, colDr, 0);                                         // next r gate, x-part: queued behind this step's candidate
+          } else {
+            mbar_acquire(&bars[kBarAX], par ^ 1);
+            issue_x(0, colDr, 0);
+          }
         }
       }
+    }
     }
   } else {
     // =========================================================== gate algebra (512 threads: one stream x 32 units each)
@@ -282,8 +358,6 @@ gru_tc_kernel(const GruTcParams p) {
     const uint32_t lane_sel = static_cast<uint32_t>(32 * quarter) << 16;
     const int u0 = kTcUnits * ublk;                                 // first hidden unit of this thread
     const uint32_t my_ah = tmem + lane_sel + colAh + 16 * ublk;     // 32 units = 16 columns
-    const int xq = p.kx / 16;                                       // layer 0: float4 chunks of x per thread
-    const uint32_t my_ax = tmem + lane_sel + colAx + (p.kx / 8) * ublk;
     const float* bR = sBias + u0;
     const float* bU = sBias + kHidden + u0;
     const float* bC = sBias + 2 * kHidden + u0;
@@ -295,7 +369,6 @@ gru_tc_kernel(const GruTcParams p) {
       const long s = tile * kTcTile + row;
       const bool ok = s < p.S;
       const long sr = ok ? s : 0;
-      const int t_end = p.t0 + p.nt;
       const int len = ok ? (p.seq_len ? p.seq_len[s] : p.n) : 0;
       const bool all_live = __all_sync(0xffffffffu, len >= t_end);   // warp-uniform: no select in the update
       float h[kTcUnits];
@@ -309,90 +382,29 @@ gru_tc_kernel(const GruTcParams p) {
           h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
         }
       }
-      // layer 0: this thread's first 16-byte chunk of step 0, the chunk strides per step and per chunk, its valid chunks
-      const int x_k0 = (p.kx / 4) * ublk;
-      int nqv = (p.in_dim - x_k0 + 3) >> 2;
-      nqv = nqv < 0 ? 0 : (nqv > xq ? xq : nqv);
-      if (!p.x_tiled && !ok) nqv = 0;                              // row-major: rows past S do not exist
-      const bool x_vec = p.x_tiled || ((p.in_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x_f32) & 15) == 0);
-      const long x_q4 = p.in_dim >> 2;
-      const long x_step = p.x_tiled ? x_q4 * kTcTile : x_q4;
-      const int x_qs = p.x_tiled ? kTcTile : 1;
-      const float4* x_base = reinterpret_cast<const float4*>(p.x_f32) +
-                             (p.x_tiled ? (tile * p.n * x_q4 + (x_k0 >> 2)) * kTcTile + row : sr * p.n * x_q4 + (x_k0 >> 2));
-      // x_t of this thread: K elements [ (kx/4)*ublk, +kx/4 ) of the row, as packed fp16 pairs (hi, and lo when split)
-      // layer 0 keeps the raw fp32 values (xf) and splits them into fp16 hi/lo only when they are written to TMEM, so
-      // the global loads issued under the u gate are not waited for until the candidate phase
-      uint32_t xr[kFirst ? 1 : 16];
-      float4 xf[kFirst ? 8 : 1];
+      // layers above the first: x_t of this thread = K elements [32*ublk, +32) of its stream's row, loaded a step ahead
+      uint32_t xr[kXSmem ? 1 : 16];
+      const uint32_t my_ax = tmem + lane_sel + colAx + 16 * ublk;
       auto load_x = [&](int t) {
-        if (!kFirst) {
+        if (!kXSmem) {
           // chunk q of stream `row` sits at ((tile*n + t)*16 + q)*128 + row: a warp reads 512 contiguous bytes
           const uint4* src = reinterpret_cast<const uint4*>(p.x_f16) + ((tile * p.n + t) * 16 + 4 * ublk) * kTcTile + row;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 v = __ldg(src + q * kTcTile);
-            xr[kFirst ? 0 : 4 * q] = v.x; xr[kFirst ? 0 : 4 * q + 1] = v.y;
-            xr[kFirst ? 0 : 4 * q + 2] = v.z; xr[kFirst ? 0 : 4 * q + 3] = v.w;
-          }
-        } else if (x_vec) {
-          // 16-byte chunks: stream-tiled mel (chunk c of stream `row` at ((tile*n + t)*Q + c)*128 + row, Q = in_dim/4) or
-          // row-major rows whose chunks are consecutive.  Base address, strides and this thread's number of chunks are
-          // fixed per tile: per step one multiply and up to 8 predicated loads
-          const float4* src = x_base + static_cast<long>(t) * x_step;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (q < nqv) v = __ldg(src + q * x_qs);
-            xf[kFirst ? q : 0] = v;
-          }
-        } else {
-          // row-major [S, n, in_dim] with in_dim % 4 != 0 or an unaligned base: element-wise with bounds (rare, slow)
-          const float* src = p.x_f32 + (sr * p.n + t) * static_cast<long>(p.in_dim) + x_k0;
-#pragma unroll 1
-          for (int q = 0; q < 8; ++q) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int k = x_k0 + 4 * q;
-            if (q < nqv) {
-              v.x = __ldg(src + 4 * q);
-              if (k + 1 < p.in_dim) v.y = __ldg(src + 4 * q + 1);
-              if (k + 2 < p.in_dim) v.z = __ldg(src + 4 * q + 2);
-              if (k + 3 < p.in_dim) v.w = __ldg(src + 4 * q + 3);
-            }
-            // (no dynamic register indexing: the loop is not unrolled)
-            if (q == 0) xf[0] = v;
-            if (kFirst) {
-              if (q == 1) xf[kFirst ? 1 : 0] = v;
-              if (q == 2) xf[kFirst ? 2 : 0] = v;
-              if (q == 3) xf[kFirst ? 3 : 0] = v;
-              if (q == 4) xf[kFirst ? 4 : 0] = v;
-              if (q == 5) xf[kFirst ? 5 : 0] = v;
-              if (q == 6) xf[kFirst ? 6 : 0] = v;
-              if (q == 7) xf[kFirst ? 7 : 0] = v;
-            }
+            xr[kXSmem ? 0 : 4 * q] = v.x; xr[kXSmem ? 0 : 4 * q + 1] = v.y;
+            xr[kXSmem ? 0 : 4 * q + 2] = v.z; xr[kXSmem ? 0 : 4 * q + 3] = v.w;
           }
         }
       };
       auto store_x = [&]() {
-        if (!kFirst) {
+        if (!kXSmem) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t v[4] = {xr[kFirst ? 0 : 4 * q], xr[kFirst ? 0 : 4 * q + 1], xr[kFirst ? 0 : 4 * q + 2],
-                                   xr[kFirst ? 0 : 4 * q + 3]};
+            const uint32_t v[4] = {xr[kXSmem ? 0 : 4 * q], xr[kXSmem ? 0 : 4 * q + 1], xr[kXSmem ? 0 : 4 * q + 2],
+                                   xr[kXSmem ? 0 : 4 * q + 3]};
             tc::st4(my_ax + 4 * q, v);
           }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q < xq) {
-              const float4 v = xf[kFirst ? q : 0];
-              const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-              tc::st2(my_ax + 2 * q, *reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-              if (split) {
-                const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
-                tc::st2(my_ax + p.kx / 2 + 2 * q, tc::pack_half2(v.x - b0.x, v.y - b0.y), tc::pack_half2(v.z - b1.x, v.w - b1.y));
-              }
-            }
         }
       };
       auto store_h = [&]() {                                       // A_h <- fp16(h)
@@ -512,19 +524,22 @@ gru_tc_kernel(const GruTcParams p) {
         }
       };
 
-      // ---- prologue: A_x <- x_0, A_h <- fp16(h).  All MMAs of the previous tile have completed (its last
-      // commit was waited for by every thread), so both operand regions are free.
-      load_x(p.t0);
-      store_x();
+      // ---- prologue: A_h <- fp16(h).  All MMAs of the previous tile have completed (its last commit was waited
+      // for by every thread), so the operand region is free.
+      if (!kXSmem) {
+        load_x(p.t0);
+        store_x();
+      }
       store_h();
       tc::wait_st();
       tc::fence_before_sync();
-      mbar_arrive(&bars[kBarAX]);
+      if (!kXSmem) mbar_arrive(&bars[kBarAX]);
       mbar_arrive(&bars[kBarAH]);
 
       for (int t = p.t0; t < t_end; ++t, ++it) {
         const uint32_t par = it & 1;
         const bool more = t + 1 < t_end;
+        if (!kXSmem && more) load_x(t + 1);                        // coalesced global loads in flight under the r gate
         const bool tl = p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && t < 64;
         // ---- r gate: keep fp16(r*h) in registers until the u-gate MMAs have finished reading A_h
         uint32_t rh[kTcUnits / 2];
@@ -558,9 +573,8 @@ gru_tc_kernel(const GruTcParams p) {
         }
         tmem_publish(&bars[kBarARH]);
         if (tl) g_tc_timeline[t * 8 + 3] = clock64();
-        if (more) load_x(t + 1);                                   // coalesced global loads in flight under the u gate
-        // ---- u gate (beside the candidate MMAs): activated in place, D_u keeps u until the update reads it
-        // (holding u in registers instead was measured slower: it pushes the gate threads past their 112 registers)
+        // ---- u gate (beside the candidate MMAs): read once, kept in registers until the update
+        float u[kTcUnits];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t v[16];
@@ -571,28 +585,28 @@ gru_tc_kernel(const GruTcParams p) {
             const float4 nb = *reinterpret_cast<const float4*>(bU + 16 * c + i);
             float2 u01, u23;
             sigmoid4_pre(u2f2(v[i], v[i + 1]), u2f2(v[i + 2], v[i + 3]), make_float2(nb.x, nb.y), make_float2(nb.z, nb.w), u01, u23);
-            v[i] = __float_as_uint(u01.x);
-            v[i + 1] = __float_as_uint(u01.y);
-            v[i + 2] = __float_as_uint(u23.x);
-            v[i + 3] = __float_as_uint(u23.y);
+            u[16 * c + i] = u01.x;
+            u[16 * c + i + 1] = u01.y;
+            u[16 * c + i + 2] = u23.x;
+            u[16 * c + i + 3] = u23.y;
           }
-          tc::st16(tmem + lane_sel + colDu + u0 + 16 * c, v);
+          if (!kXSmem && c == 0 && more) {
+            // next step's x: the x-part MMAs of this step were committed right behind the u gate, so A_x is free by now;
+            // stored between the halves of the u gate so that x and the whole u are never in registers together
+            mbar_acquire(&bars[kBarXD], par);
+            store_x();
+            tmem_publish(&bars[kBarAX]);
+          }
         }
-        tc::wait_st();
         // ---- candidate and state update: only what the next step's MMAs wait for
         if (tl) g_tc_timeline[t * 8 + 4] = clock64();
         mbar_acquire(&bars[kBarC], par);
         if (tl) g_tc_timeline[t * 8 + 5] = clock64();
-        if (more) {                                                // next step's x first: its r-gate MMAs run under this phase
-          store_x();
-          tmem_publish(&bars[kBarAX]);
-        }
         const bool live = t < len;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t vc[16], vu[16];
+          uint32_t vc[16];
           tc::ld16(tmem + lane_sel + colDc + u0 + 16 * c, vc);
-          tc::ld16(tmem + lane_sel + colDu + u0 + 16 * c, vu);
           tc::wait_ld();
           uint32_t packed[8];
 #pragma unroll
@@ -603,8 +617,8 @@ gru_tc_kernel(const GruTcParams p) {
             tanh4_pre(u2f2(vc[i], vc[i + 1]), u2f2(vc[i + 2], vc[i + 3]), make_float2(pb.x, pb.y), make_float2(pb.z, pb.w), c01, c23);
             const float2 neg = make_float2(-1.0f, -1.0f);
             const float2 h01 = make_float2(h[j], h[j + 1]), h23 = make_float2(h[j + 2], h[j + 3]);
-            float2 n01 = __ffma2_rn(u2f2(vu[i], vu[i + 1]), __ffma2_rn(c01, neg, h01), c01);          // u*h + (1-u)*c
-            float2 n23 = __ffma2_rn(u2f2(vu[i + 2], vu[i + 3]), __ffma2_rn(c23, neg, h23), c23);
+            float2 n01 = __ffma2_rn(make_float2(u[j], u[j + 1]), __ffma2_rn(c01, neg, h01), c01);          // u*h + (1-u)*c
+            float2 n23 = __ffma2_rn(make_float2(u[j + 2], u[j + 3]), __ffma2_rn(c23, neg, h23), c23);
             if (!all_live) {                                       // dynamic_rnn: state carried past the length
               n01 = live ? n01 : h01;
               n23 = live ? n23 : h23;
@@ -623,7 +637,7 @@ gru_tc_kernel(const GruTcParams p) {
         // ---- outputs of this step, in the shadow of the next step's r-gate MMAs.  dynamic_rnn: zero output past the length
         const bool emit = all_live || live;
         if (!kLast) {
-          // tiled hand-off (rows past S are written too: the scratch is padded to whole tiles)
+          // the next layer's x operand, row-tiled (rows past S are written too: the scratch is padded to whole tiles)
           uint4* dst = reinterpret_cast<uint4*>(p.y_f16) + ((tile * p.n + t) * 16 + 4 * ublk) * kTcTile + row;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -651,10 +665,32 @@ gru_tc_kernel(const GruTcParams p) {
   if (warp == kMmaWarp) tc::tmem_dealloc(tmem, 512);
 }
 
-
-static size_t gru_tc_smem_bytes(int ktot, bool last) {
-  return static_cast<size_t>(384) * ktot * 2 + sizeof(float) * (384 + 3 * kTcTile * 8 + kHidden * kTcMaxClasses) +
-         (last ? sizeof(float) * 4 * 6 * kTcTile : 0) + kNumBars * sizeof(uint64_t) + 16;
+static size_t gru_tc_smem_bytes(int kxw, bool last, int nbuf) {
+  return static_cast<size_t>(768) * (kxw + kHidden) + static_cast<size_t>(nbuf) * (kxw / 8) * tc::kTileChunkBytes +
+         sizeof(float) * 384 + (last ? sizeof(float) * (3 * kTcTile * 8 + kHidden * kTcMaxClasses + 4 * 6 * kTcTile) : 0) +
+         kNumBars * sizeof(uint64_t) + 16;
+}
+static size_t max_dynamic_smem(int device) {
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+  return static_cast<size_t>(v);
+}
+// x buffers the kernel can keep for a layer with `kxw` operand columns: 2, 1, or 0 (the layer does not fit at all)
+static int gru_tc_x_buffers(int kxw, bool last, int device) {
+  const size_t cap = max_dynamic_smem(device);
+  if (gru_tc_smem_bytes(kxw, last, 2) <= cap) return 2;
+  if (gru_tc_smem_bytes(kxw, last, 1) <= cap) return 1;
+  return 0;
+}
+// the x product of a first layer of `in_dim` inputs can be split (x_hi/x_lo operand, Wx_hi/Wx_lo weights)
+bool gru_tc_can_split(int in_dim, bool last, int device) {
+  const int kx = (in_dim + 15) / 16 * 16;
+  return gru_tc_x_buffers(2 * kx, last, device) > 0;
+}
+// first layer: weights + at least one x buffer; the layers above (128 inputs through TMEM) always fit
+bool gru_tc_layer_fits(int in_dim, bool split, bool last, int device) {
+  const int kx = (in_dim + 15) / 16 * 16;
+  return gru_tc_x_buffers(split ? 2 * kx : kx, last, device) > 0;
 }
 
 // Pack one layer's TF kernels into the fp16 canonical [384, kxw+128] B operand: [Wx_hi | Wx_lo (split) | Wh].
@@ -687,6 +723,35 @@ void pack_tc_weights(const float* gates_kernel, const float* cand_kernel, int in
   *kxw_out = kxw;
 }
 
+// Callers that hold x as row-major fp32 [S, n, in_dim] (kws_gru_forward): the row-tiled fp16 operand the kernel copies,
+// [tile][t][x_hi chunks | x_lo chunks (split)][128 streams][8].  The streaming and deployment paths never run this: their
+// front end writes the operand itself.
+__global__ void __launch_bounds__(256)
+tc_pack_x_kernel(const float* __restrict__ x, long S, int n, int in_dim, int nc, int split, uint4* __restrict__ out) {
+  const long ntiles = (S + kTcTile - 1) / kTcTile;
+  const long total = ntiles * n * nc * kTcTile;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i & (kTcTile - 1));
+    long r = i >> 7;
+    const int c = static_cast<int>(r % nc);
+    r /= nc;
+    const int t = static_cast<int>(r % n);
+    const long tile = r / n;
+    const long s = tile * kTcTile + row;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = 8 * c + j;
+      v[j] = (s < S && k < in_dim) ? __ldg(x + (s * n + t) * static_cast<long>(in_dim) + k) : 0.0f;
+    }
+    uint4 hi, lo;
+    tc::split_half8(v, &hi, &lo);
+    const long base = (tile * n + t) * static_cast<long>(split ? 2 * nc : nc);
+    out[(base + c) * kTcTile + row] = hi;
+    if (split) out[(base + nc + c) * kTcTile + row] = lo;
+  }
+}
+
 int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
   if (a.S <= 0) return KWS_OK;
   if (m->cfg.num_classes > kTcMaxClasses)
@@ -705,19 +770,43 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
   const long ntiles = ceil_div(a.S, kTcTile);
   const size_t per_buf = static_cast<size_t>(ntiles) * kTcTile * a.n * kHidden;     // halves (whole tiles)
   __half* seq = reinterpret_cast<__half*>(a.seq_scratch ? a.seq_scratch : m->scratch_seq);
+  // layer 0's operand: written by the front end (x_tiled), or packed here from the caller's row-major fp32 x
+  const unsigned char* x0 = reinterpret_cast<const unsigned char*>(a.x);
+  if (!a.x_tiled) {
+    const int nc = m->layer[0].tc_kx / 8;
+    const bool split = m->layer[0].tc_kxw != m->layer[0].tc_kx;
+    const size_t need = static_cast<size_t>(ntiles) * a.n * (m->layer[0].tc_kxw / 8) * tc::kTileChunkBytes;
+    if (need > m->tc_xt_bytes) {
+      KWS_CUDA_OK(cudaStreamSynchronize(st));                          // the old buffer may still be read
+      cudaFree(m->tc_xt);
+      m->tc_xt = nullptr;
+      m->tc_xt_bytes = 0;
+      if (cudaMalloc(&m->tc_xt, need) != cudaSuccess)
+        return fail(KWS_ERR_ALLOC, "x operand scratch of %zu bytes: allocation failed", need);
+      m->tc_xt_bytes = need;
+    }
+    const long total = ntiles * a.n * nc * kTcTile;
+    const long blocks = std::min<long>(ceil_div(total, 256), static_cast<long>(sm_count()) * 16);
+    tc_pack_x_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(a.x, a.S, a.n, m->layer[0].in_dim, nc, split ? 1 : 0,
+                                                                    static_cast<uint4*>(m->tc_xt));
+    KWS_LAUNCH_OK("tc_pack_x_kernel");
+    x0 = static_cast<const unsigned char*>(m->tc_xt);
+  }
   // frames [t0, t0 + nt) of layer l on stream `cs`; `head` = the first chunk of the sequence (incoming state, VAD reset)
   auto launch_layer = [&](int l, int t0, int nt, bool head, cudaStream_t cs) -> int {
     const bool last = l == L - 1;
     GruTcParams p;
     p.kx = m->layer[l].tc_kx;
     p.kxw = m->layer[l].tc_kxw;
-    p.in_dim = m->layer[l].in_dim;
+    p.nbuf = l == 0 ? gru_tc_x_buffers(p.kxw, last, m->device) : 1;
+    if (p.nbuf == 0)
+      return fail(KWS_ERR_UNSUPPORTED, "layer %d (%d inputs) does not fit the tensor-core recurrent kernel's shared memory", l,
+                  m->layer[l].in_dim);
     p.S = a.S;
     p.n = a.n;
     p.t0 = t0;
     p.nt = nt;
-    p.x_f32 = l == 0 ? a.x : nullptr;
-    p.x_tiled = l == 0 && a.x_tiled ? 1 : 0;
+    p.x_tiles = l == 0 ? x0 : nullptr;
     p.x_f16 = l == 0 ? nullptr : seq + ((l - 1) & 1) * per_buf;
     p.y_f16 = last ? nullptr : seq + (l & 1) * per_buf;
     p.wpack = static_cast<const __half*>(m->layer[l].tc_wpack);
@@ -726,8 +815,6 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     p.h_in = head ? a.state_in + static_cast<long>(l) * a.S * kHidden : p.h_out;
     p.seq_len = a.seq_len;
     p.zero_state = head ? a.zero_state : nullptr;
-    p.fc_w = m->fc_w;
-    p.fc_b = m->fc_b;
     p.C = m->cfg.num_classes;
     p.probs = a.probs;
     p.logits = a.logits;
@@ -735,17 +822,19 @@ int launch_gru_tc(kws_model* m, const GruArgs& a, cudaStream_t st) {
     for (int j = 0; j < kHidden; ++j)
       for (int c = 0; c < kTcMaxClasses; ++c) p.fcw[j * kTcMaxClasses + c] = c < m->cfg.num_classes ? m->fc_w_host[j * m->cfg.num_classes + c] : 0.0f;
     for (int c = 0; c < kTcMaxClasses; ++c) p.fcb[c] = c < m->cfg.num_classes ? m->fc_b_host[c] : 0.0f;
-    const size_t smem = gru_tc_smem_bytes(p.kxw + kHidden, last);
+    const size_t smem = gru_tc_smem_bytes(p.kxw, last, l == 0 ? p.nbuf : 0);
     const long blocks = ntiles < sm_count() ? ntiles : sm_count();
-    const bool first = l == 0;
     auto launch = [&](auto kernel) -> int {
       KWS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
       kernel<<<static_cast<unsigned>(blocks), kTcThreads, smem, cs>>>(p);
       return KWS_OK;
     };
+    // straight-line issue code for the shapes of the deployment model; another mel count takes its trip counts from p
+    const bool mel40 = p.kx == 48 && p.kxw == 96;
     int rc;
-    if (last) rc = first ? launch(gru_tc_kernel<true, true>) : launch(gru_tc_kernel<true, false>);
-    else rc = first ? launch(gru_tc_kernel<false, true>) : launch(gru_tc_kernel<false, false>);
+    if (l > 0) rc = last ? launch(gru_tc_kernel<true, false, 8>) : launch(gru_tc_kernel<false, false, 8>);
+    else if (last) rc = mel40 ? launch(gru_tc_kernel<true, true, 3>) : launch(gru_tc_kernel<true, true, 0>);
+    else rc = mel40 ? launch(gru_tc_kernel<false, true, 3>) : launch(gru_tc_kernel<false, true, 0>);
     if (rc != KWS_OK) return rc;
     KWS_LAUNCH_OK("gru_tc_kernel");
     return KWS_OK;

@@ -8,6 +8,10 @@
 //   * A operand (activations) in TMEM ("TS" form): row m on lane m, two fp16 per 32-bit column,
 //     element (m, k) in column k/2, low half = even k.  The thread that owns TMEM lane m (= stream m
 //     of the tile) writes its own row with tcgen05.st, so no shared-memory staging or proxy fence.
+//   * A operand in shared memory ("SS" form) where it arrives by bulk copy: the row-tiled layout
+//     [K/8 chunks][128 rows][8 elements] (kTileChunkBytes = 2048 per chunk), i.e. the same core matrices with
+//     LBO = 2048 (K direction), SBO = 128 (M direction).  It is what the layers hand to each other in HBM, so one
+//     contiguous copy of (K/8)*2048 bytes is an MMA-ready operand.
 //   * D accumulators fp32 in TMEM, row m on lane m, one column per n.
 #pragma once
 
@@ -62,6 +66,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(addr, parity); ++spins) {
     if (spins > (1u << 24)) __trap();
   }
+}
+
+// ---- bulk async copy (TMA without a tensor map): `bytes` contiguous bytes global -> shared through the async proxy,
+// completion counted on an mbarrier whose pending transaction count was raised by mbar_arrive_expect_tx.
+// Source, destination and size are multiples of 16 bytes.  SASS: UBLKCP.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---- descriptors
@@ -169,10 +186,30 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// 8 fp32 values -> 8 fp16 roundings (hi) and the 8 fp16 roundings of what they lost (lo): x = hi + lo to 2^-22 relative
+__device__ __forceinline__ void split_half8(const float (&v)[8], uint4* hi, uint4* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 b = __half22float2(hh);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = pack_half2(v[2 * i] - b.x, v[2 * i + 1] - b.y);
+  }
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // byte offset of element (n, k) of a [N, K] fp16 matrix in the canonical K-major SWIZZLE_NONE layout
 __host__ __device__ constexpr size_t canon_offset(int n, int k, int K) {
   return static_cast<size_t>(n / 8) * (static_cast<size_t>(K / 8) * 128) + static_cast<size_t>(k / 8) * 128 +
          static_cast<size_t>(n % 8) * 16 + static_cast<size_t>(k % 8) * 2;
+}
+
+// row-tiled A operand (see the conventions above): byte offset of element (m, k) of a [128, K] fp16 tile
+constexpr uint32_t kTileChunkBytes = 2048;
+__host__ __device__ constexpr size_t tile_offset(int m, int k) {
+  return static_cast<size_t>(k / 8) * kTileChunkBytes + static_cast<size_t>(m) * 16 + static_cast<size_t>(k % 8) * 2;
 }
 
 // byte offset of element (n, k) of a [N, K] fp16 matrix in the canonical MN-major SWIZZLE_NONE layout

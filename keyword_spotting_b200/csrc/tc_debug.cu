@@ -9,9 +9,10 @@ namespace kws {
 
 __global__ void __launch_bounds__(128, 1)
 tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bpacked, float* __restrict__ D, int N,
-                    int K, int ss_mode) {
+                    int K, int ss_mode, __half* __restrict__ Atile) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar_tx;
   __shared__ uint32_t tmem_base_smem;
   unsigned char* sB = smem;                                   // [N, K] fp16 canonical
   unsigned char* sA = smem + static_cast<size_t>(N) * K * 2;  // [128, K] fp16 canonical (SS form only)
@@ -20,6 +21,7 @@ tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bpac
   if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 512);
   if (tid == 0) {
     tc::mbar_init(&bar, 1);
+    tc::mbar_init(&bar_tx, 1);
     tc::mbar_fence_init();
   }
   const int b16 = N * K * 2 / 16;
@@ -32,7 +34,26 @@ tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bpac
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t a_col = 256;
   const float* arow = A + static_cast<size_t>(tid) * K;
-  if (ss_mode) {
+  if (ss_mode == 3) {
+    // A takes the production route of the recurrent kernel: written to global memory in the row-tiled layout
+    // (tc::tile_offset), then ONE bulk copy into shared memory, completion on an mbarrier
+    for (int k8 = 0; k8 < K / 8; ++k8) {
+      uint4 v;
+      v.x = tc::pack_half2(arow[8 * k8 + 0], arow[8 * k8 + 1]);
+      v.y = tc::pack_half2(arow[8 * k8 + 2], arow[8 * k8 + 3]);
+      v.z = tc::pack_half2(arow[8 * k8 + 4], arow[8 * k8 + 5]);
+      v.w = tc::pack_half2(arow[8 * k8 + 6], arow[8 * k8 + 7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(Atile) + tc::tile_offset(tid, 8 * k8)) = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(K / 8) * tc::kTileChunkBytes;
+      tc::mbar_arrive_expect_tx(&bar_tx, bytes);
+      tc::bulk_g2s(sA, Atile, bytes, &bar_tx);
+    }
+    tc::mbar_wait(&bar_tx, 0);
+  } else if (ss_mode) {
     for (int k8 = 0; k8 < K / 8; ++k8) {
       uint4 v;
       v.x = tc::pack_half2(arow[8 * k8 + 0], arow[8 * k8 + 1]);
@@ -59,7 +80,10 @@ tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bpac
     const uint32_t sbo = static_cast<uint32_t>(K / 8) * 128;
     for (int k16 = 0; k16 < K / 16; ++k16) {
       const uint64_t bdesc = tc::smem_desc(tc::smem_u32(sB) + k16 * 256, 128, sbo);
-      if (ss_mode) {
+      if (ss_mode == 3) {
+        const uint64_t adesc = tc::smem_desc(tc::smem_u32(sA) + k16 * 2 * tc::kTileChunkBytes, tc::kTileChunkBytes, 128);
+        tc::mma_ss(tmem, adesc, bdesc, idesc, k16 > 0);
+      } else if (ss_mode) {
         const uint64_t adesc = tc::smem_desc(tc::smem_u32(sA) + k16 * 256, 128, sbo);
         tc::mma_ss(tmem, adesc, bdesc, idesc, k16 > 0);
       } else {
@@ -85,7 +109,8 @@ tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bpac
 
 }  // namespace kws
 
-// ss_mode: 0 = A in TMEM, 1 = A in shared memory, 2 = A in shared memory and B in the MN-major layout.
+// ss_mode: 0 = A in TMEM, 1 = A in shared memory, 2 = A in shared memory and B in the MN-major layout, 3 = A in the
+// row-tiled layout in global memory, brought to shared memory by one bulk copy (the recurrent kernel's x operand).
 // A [128, K] fp32 (rounded to fp16 on the device), B [N, K] fp32 (rounded and packed on the host side of
 // this call) -> D [128, N] fp32 = A * B^T with fp32 accumulation.  N % 16 == 0, N <= 256, K % 32 == 0, K <= 256.
 extern "C" int kws_debug_tc_gemm(const float* A, const float* B_host, float* D, int N, int K, int ss_mode,
@@ -102,14 +127,23 @@ extern "C" int kws_debug_tc_gemm(const float* A, const float* B_host, float* D, 
       *reinterpret_cast<__half*>(&packed[ss_mode == 2 ? tc::canon_offset_mn(n, k, K) : tc::canon_offset(n, k, K)]) = h;
     }
   __half* dB = nullptr;
+  __half* dA = nullptr;
   KWS_CUDA_OK(cudaMalloc(&dB, packed.size()));
+  if (ss_mode == 3) {
+    const cudaError_t ea = cudaMalloc(&dA, static_cast<size_t>(128) * K * 2);
+    if (ea != cudaSuccess) {
+      cudaFree(dB);
+      return fail(KWS_ERR_ALLOC, "tc_gemm_test_kernel: %s", cudaGetErrorString(ea));
+    }
+  }
   KWS_CUDA_OK(cudaMemcpy(dB, packed.data(), packed.size(), cudaMemcpyHostToDevice));
   const size_t smem = static_cast<size_t>(N) * K * 2 + static_cast<size_t>(128) * K * 2;
   KWS_CUDA_OK(cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  tc_gemm_test_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, dB, D, N, K, ss_mode);
+  tc_gemm_test_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, dB, D, N, K, ss_mode, dA);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
   cudaFree(dB);
+  cudaFree(dA);
   if (e != cudaSuccess) return fail(KWS_ERR_CUDA, "tc_gemm_test_kernel failed: %s", cudaGetErrorString(e));
   return KWS_OK;
 }

@@ -5,7 +5,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("ss_mode", [0, 1, 2])      # 2: B operand in the MN-major layout (front end GEMM2)
+@pytest.mark.parametrize("ss_mode", [0, 1, 2, 3])   # 2: B operand MN-major; 3: A row-tiled in HBM, bulk-copied to smem (GRU x operand)
 @pytest.mark.parametrize("N,K", [(16, 32), (32, 256), (128, 128), (256, 256), (128, 160), (256, 64)])
 def test_tc_gemm_layouts(N, K, ss_mode):
     import torch

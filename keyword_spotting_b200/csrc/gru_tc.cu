@@ -55,6 +55,7 @@ constexpr int kTcEpiWarps = 16;           // warps 0-15: gate algebra.  Warp w o
 constexpr int kTcEpiThreads = 32 * kTcEpiWarps;   //   and the 32 hidden units [32*(w/4), +32) of those streams
 constexpr int kTcThreads = kTcEpiThreads + 128;   // + warpgroup 4: warp 16 issues the x copies and the MMAs (warps 17-19 only donate registers)
 constexpr int kTcUnits = 32;              // hidden units per gate thread
+constexpr int kFcOperandBytes = 16 * kHidden * 2;   // FC weights as an MMA operand: N = 16 (8 classes, hi and lo), K = 128
 
 
 struct GruTcParams {
@@ -173,7 +174,7 @@ __device__ __forceinline__ void mbar_acquire(uint64_t* bar, uint32_t parity) {
 __device__ long long g_tc_timeline[64 * 8];
 static int g_tc_timeline_on = 0;
 
-enum { kBarXF0 = 0, kBarXF1, kBarAX, kBarXD, kBarAH, kBarARH, kBarR, kBarU, kBarC, kNumBars };
+enum { kBarXF0 = 0, kBarXF1, kBarAX, kBarXD, kBarAH, kBarARH, kBarR, kBarU, kBarC, kBarF, kBarFR, kNumBars };
 
 // kXSmem: the x operand arrives in shared memory by bulk copy (layer 0: 24 KB per tile-step next to 172 KB of weights).
 //   The layers above (32 KB per tile-step next to 196 KB of weights: no room) take x through the gate threads into
@@ -189,10 +190,10 @@ gru_tc_kernel(const GruTcParams p) {
   unsigned char* sW = smem;                                                         // [384, ktot] fp16
   unsigned char* sX = sW + static_cast<size_t>(768) * ktot;                         // kXSmem: [nbuf][kxw/8 chunks][128][8] fp16
   float* sBias = reinterpret_cast<float*>(sX + (kXSmem ? static_cast<size_t>(p.nbuf) * xbytes : 0));   // [384] pre-scaled
-  float* sXch = sBias + 384;                                               // [3][128][8] FC partials of unit blocks 1..3 (last layer)
-  float* sFc = sXch + 3 * kTcTile * kTcMaxClasses;                         // [128][8] FC weights (last layer)
-  float* sProb = sFc + kHidden * kTcMaxClasses;                            // [4 steps][6][128] parked probabilities (last layer)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kLast ? sProb + 4 * 6 * kTcTile : sBias + 384);   // [kNumBars]
+  unsigned char* sWfc = reinterpret_cast<unsigned char*>(sBias + 384);     // [16, 128] fp16 canonical: FC weights, rows 0-7 hi, 8-15 lo (last layer)
+  float* sProb = reinterpret_cast<float*>(sWfc + kFcOperandBytes);         // [4 steps][6][128] parked probabilities (last layer)
+  float* sLg = sProb + 4 * 6 * kTcTile;                                    // [8][128] logits between their read and the softmax (last layer)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kLast ? sLg + kTcMaxClasses * kTcTile : sBias + 384);   // [kNumBars]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -209,6 +210,8 @@ gru_tc_kernel(const GruTcParams p) {
     tc::mbar_init(&bars[kBarR], 1);
     tc::mbar_init(&bars[kBarU], 1);
     tc::mbar_init(&bars[kBarC], 1);
+    tc::mbar_init(&bars[kBarF], 1);
+    tc::mbar_init(&bars[kBarFR], kTcTile);          // the 128 threads of unit block 0 read the logits
     tc::mbar_fence_init();
   }
   {
@@ -217,8 +220,13 @@ gru_tc_kernel(const GruTcParams p) {
     for (int i = tid; i < n16; i += kTcThreads) reinterpret_cast<uint4*>(sW)[i] = __ldg(src + i);
     for (int i = tid; i < 384; i += kTcThreads)
       sBias[i] = p.bias[i] * (i < 2 * kHidden ? -kLog2e : 2.0f * kLog2e);
-    if (kLast)
-      for (int i = tid; i < kHidden * kTcMaxClasses; i += kTcThreads) sFc[i] = p.fcw[i];
+    if (kLast)                                       // B operand of the FC: row c = fp16(W[:, c]), row 8 + c = what that rounding lost
+      for (int i = tid; i < 16 * kHidden; i += kTcThreads) {
+        const int n = i >> 7, k = i & (kHidden - 1);
+        const float w = p.fcw[k * kTcMaxClasses + (n & 7)];
+        const __half hi = __float2half_rn(w);
+        *reinterpret_cast<__half*>(sWfc + tc::canon_offset(n, k, kHidden)) = n < 8 ? hi : __float2half_rn(w - __half2float(hi));
+      }
   }
   tc::fence_proxy_async();            // weights written with generic stores, read by the MMA (async proxy)
   tc::fence_before_sync();
@@ -299,7 +307,27 @@ gru_tc_kernel(const GruTcParams p) {
                      &bars[kBarXF0 + buf]);
       }
     };
+    // FC on the tensor core (last layer): logits(t) = h'(t) Wfc with h' = hi + lo (two fp16 terms, exact to 2^-22) and
+    // Wfc = hi + lo packed as the 16 rows of one N = 16 operand: D_fc[c] + D_fc[8 + c].  A_hi is A_h (the next step's
+    // recurrent operand anyway); A_lo is parked by the gate threads in the columns of D_u they own (free between the
+    // u gate's read and the next u-gate MMAs, which are issued behind these); D_fc borrows candidate columns 0..15
+    // (free until the next candidate x-part, which waits for the logits to be read: kBarFR).
+    const uint32_t idesc16 = tc::idesc_f16(128, 16);
+    const uint64_t fdesc = tc::smem_desc(tc::smem_u32(sWfc), 128, (kHidden / 8) * 128);
+    uint64_t fd = fdesc;
+    auto issue_fc = [&]() {
+#ifndef KWS_ABL_NOFCMMA
+#pragma unroll
+      for (int j = 0; j < kHidden / 16; ++j)
+        if (lead) tc::mma_ts(tm + colDc, tm + colAh + 8 * j, fd + 16 * j, idesc16, j > 0);
+#pragma unroll
+      for (int j = 0; j < kHidden / 16; ++j)
+        if (lead) tc::mma_ts(tm + colDc, tm + colDu + 32 * (j >> 1) + 8 * (j & 1), fd + 16 * j, idesc16, true);
+#endif
+      if (lead) tc::commit(&bars[kBarF]);
+    };
     uint32_t it = 0;                                                       // (tile, step) pairs done by this CTA
+    uint32_t ah = 0, nf = 0;                                               // A_h hand-overs consumed, FC products issued
     if (static_cast<long>(blockIdx.x) < ntiles && p.nt > 0) {
       if (kXSmem) {
         prefetch(blockIdx.x, p.t0, 0);
@@ -313,23 +341,39 @@ gru_tc_kernel(const GruTcParams p) {
       for (int t = p.t0; t < t_end; ++t, ++it) {
         const uint32_t par = it & 1;
         const int buf = two ? static_cast<int>(it & 1) : 0;
-        asm volatile("" : "+r"(tm), "+l"(wb), "+l"(xd0), "+l"(xd1));
+        asm volatile("" : "+r"(tm), "+l"(wb), "+l"(xd0), "+l"(xd1), "+l"(fd));
         const bool step_next = t + 1 < t_end;
         const long ntile = step_next ? tile : tile + gridDim.x;            // what this CTA runs next
         const int nt1 = step_next ? t + 1 : p.t0;
         const bool has_next = ntile < ntiles;
-        mbar_acquire(&bars[kBarAH], par);                                  // h_{t-1} in A_h; every MMA of the previous step is complete
+        mbar_acquire(&bars[kBarAH], ah & 1);                               // h_{t-1} in A_h; every MMA of the previous step is complete
+        ++ah;
         issue_h(colDr, 0);
         if (lead) tc::commit(&bars[kBarR]);
+        if (kLast && t > p.t0) {                                           // logits of the previous step, behind the critical r gate
+          issue_fc();
+          ++nf;
+        }
         if (kXSmem && two && has_next) prefetch(ntile, nt1, buf ^ 1);      // the other buffer's last readers were the previous step's MMAs
+#ifdef KWS_L2_PREFETCH
+        if (!kXSmem && lead && t + KWS_L2_PREFETCH < t_end)                // the gate threads' x loads of a later step: HBM -> L2 now
+          tc::bulk_prefetch_l2(p.x_f16 + (tile * p.n + t + KWS_L2_PREFETCH) * static_cast<long>(16 * kTcTile * 8), 16 * tc::kTileChunkBytes);
+#endif
         issue_x(buf, colDu, 1);                                            // u gate
         issue_h(colDu, 1);
         if (lead) tc::commit(&bars[kBarU]);
+        if (kLast && nf > 0) mbar_acquire(&bars[kBarFR], (nf - 1) & 1);    // the logits have left the candidate columns
         issue_x(buf, colDc, 2);                                            // candidate, x-part
         if (!kXSmem && lead) tc::commit(&bars[kBarXD]);                    // A_x has been read: the gate threads may store x_{t+1}
         mbar_acquire(&bars[kBarARH], par);                                 // r*h in A_h (and D_r read by every gate thread)
         issue_h(colDc, 2);
         if (lead) tc::commit(&bars[kBarC]);
+        if (kLast && !step_next) {                                         // the tile's last step: its logits are not followed by an r gate
+          mbar_acquire(&bars[kBarAH], ah & 1);
+          ++ah;
+          issue_fc();
+          ++nf;
+        }
         if (has_next) {
           if (kXSmem) {
             int nb = buf ^ 1;
@@ -358,6 +402,8 @@ gru_tc_kernel(const GruTcParams p) {
     const uint32_t lane_sel = static_cast<uint32_t>(32 * quarter) << 16;
     const int u0 = kTcUnits * ublk;                                 // first hidden unit of this thread
     const uint32_t my_ah = tmem + lane_sel + colAh + 16 * ublk;     // 32 units = 16 columns
+    const uint32_t my_alo = tmem + lane_sel + colDu + 32 * ublk;    // last layer: fp16(h' - fp16(h')) in the first 16 of this thread's own D_u columns
+    uint32_t nf = 0;                                                // FC products consumed
     const float* bR = sBias + u0;
     const float* bU = sBias + kHidden + u0;
     const float* bC = sBias + 2 * kHidden + u0;
@@ -386,7 +432,11 @@ gru_tc_kernel(const GruTcParams p) {
       uint32_t xr[kXSmem ? 1 : 16];
       const uint32_t my_ax = tmem + lane_sel + colAx + 16 * ublk;
       auto load_x = [&](int t) {
+#ifdef KWS_ABL_NOX1
+        if (false) {
+#else
         if (!kXSmem) {
+#endif
           // chunk q of stream `row` sits at ((tile*n + t)*16 + q)*128 + row: a warp reads 512 contiguous bytes
           const uint4* src = reinterpret_cast<const uint4*>(p.x_f16) + ((tile * p.n + t) * 16 + 4 * ublk) * kTcTile + row;
 #pragma unroll
@@ -398,7 +448,11 @@ gru_tc_kernel(const GruTcParams p) {
         }
       };
       auto store_x = [&]() {
+#ifdef KWS_ABL_NOX1
+        if (false) {
+#else
         if (!kXSmem) {
+#endif
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t v[4] = {xr[kXSmem ? 0 : 4 * q], xr[kXSmem ? 0 : 4 * q + 1], xr[kXSmem ? 0 : 4 * q + 2],
@@ -416,113 +470,71 @@ gru_tc_kernel(const GruTcParams p) {
           tc::st8(my_ah + 8 * c, v);
         }
       };
-      // FC + softmax of a step are computed right after its h' has been published, i.e. while the next step's
-      // r-gate MMAs run: 32 units per thread, partial sums of unit blocks 1..3 handed to block 0 through smem.
-      auto fc_finish = [&](int t_done, bool emit) {
-        const bool tl2 = p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && t_done < 32;
-        // class pairs (2c, 2c+1) are accumulated with packed FFMA2: h[j] broadcast x a weight pair; the [128][8] weights
-        // sit in shared memory and every lane reads the same row (broadcast, one wavefront per load)
-        float2 part2[kTcMaxClasses / 2];
+      // Last layer: the logits of a step come out of the tensor core during the NEXT step (issue_fc above); the 128 threads
+      // of unit block 0 read them (16 TMEM columns: hi-weight and lo-weight halves), release the columns and finish
+      // softmax + stores in the shadow of the candidate MMAs.  dynamic_rnn: zero output past the length, i.e. logits = bias.
+      auto read_logits = [&](uint32_t fpar, bool emit) {
+        mbar_acquire(&bars[kBarF], fpar);
+        uint32_t v[16];
+        tc::ld16(tmem + lane_sel + colDc, v);
+        tc::wait_ld();
+        tc::fence_before_sync();
+        mbar_arrive(&bars[kBarFR]);
 #pragma unroll
-        for (int c = 0; c < kTcMaxClasses / 2; ++c) part2[c] = make_float2(0.0f, 0.0f);
-        if (emit) {                                                 // dynamic_rnn: zero output past the length
-          const float4* wrow = reinterpret_cast<const float4*>(sFc + u0 * kTcMaxClasses);
-          if (p.C <= 6) {                                           // the model's 6 classes: 3 pairs
+        for (int c = 0; c < kTcMaxClasses; ++c)          // parked in shared memory (this thread's column): 8 registers less under the r*h hand-over
+          sLg[c * kTcTile + row] = (emit ? __uint_as_float(v[c]) + __uint_as_float(v[8 + c]) : 0.0f) + p.fcb[c];
+      };
+      auto emit_probs = [&](int t_done) {
+        if (!ok) return;
+        float lg[kTcMaxClasses];
+        float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < kTcUnits; ++j) {
-              const float4 wa = wrow[2 * j];
-              const float2 wb = *reinterpret_cast<const float2*>(wrow + 2 * j + 1);
-              const float2 hh = make_float2(h[j], h[j]);
-              part2[0] = __ffma2_rn(hh, make_float2(wa.x, wa.y), part2[0]);
-              part2[1] = __ffma2_rn(hh, make_float2(wa.z, wa.w), part2[1]);
-              part2[2] = __ffma2_rn(hh, wb, part2[2]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < kTcUnits; ++j) {
-              const float4 wa = wrow[2 * j], wb = wrow[2 * j + 1];
-              const float2 hh = make_float2(h[j], h[j]);
-              part2[0] = __ffma2_rn(hh, make_float2(wa.x, wa.y), part2[0]);
-              part2[1] = __ffma2_rn(hh, make_float2(wa.z, wa.w), part2[1]);
-              part2[2] = __ffma2_rn(hh, make_float2(wb.x, wb.y), part2[2]);
-              part2[3] = __ffma2_rn(hh, make_float2(wb.z, wb.w), part2[3]);
-            }
-          }
+        for (int c = 0; c < 8; ++c) {
+          lg[c] = sLg[c * kTcTile + row];
+          if (c < p.C) mx = fmaxf(mx, lg[c]);
         }
-        const float part[kTcMaxClasses] = {part2[0].x, part2[0].y, part2[1].x, part2[1].y,
-                                           part2[2].x, part2[2].y, part2[3].x, part2[3].y};
-        if (tl2) g_tc_timeline[256 + t_done * 4 + 0] = clock64();
-        if (ublk > 0) {
-          float* dst = sXch + ((ublk - 1) * kTcTile + row) * 8;
-          *reinterpret_cast<float4*>(dst) = make_float4(part[0], part[1], part[2], part[3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(part[4], part[5], part[6], part[7]);
-          asm volatile("bar.arrive 1, 512;" ::: "memory");
-        } else {
-          asm volatile("bar.sync 1, 512;" ::: "memory");
-          if (tl2) g_tc_timeline[256 + t_done * 4 + 1] = clock64();
-          if (ok) {
-            float lg[8];
-            float mx = -INFINITY;
-            {
-              // the three other unit blocks' partial sums: 16-byte reads (a row is 32 bytes: conflict-free)
-              float o[3][8];
+        float e[8], sum = 0.0f;
 #pragma unroll
-              for (int b = 0; b < 3; ++b) {
-                const float4 lo4 = *reinterpret_cast<const float4*>(sXch + (b * kTcTile + row) * 8);
-                const float4 hi4 = *reinterpret_cast<const float4*>(sXch + (b * kTcTile + row) * 8 + 4);
-                o[b][0] = lo4.x; o[b][1] = lo4.y; o[b][2] = lo4.z; o[b][3] = lo4.w;
-                o[b][4] = hi4.x; o[b][5] = hi4.y; o[b][6] = hi4.z; o[b][7] = hi4.w;
-              }
+        for (int c = 0; c < 8; ++c) {
+          e[c] = c < p.C ? ex2_approx((lg[c] - mx) * kLog2e) : 0.0f;    // 2 ulp: far inside the 1e-3 contract
+          sum += e[c];
+        }
+        const float inv = rcp_approx(sum);                              // sum in [1, C]
+        if (probs_batched) {
+          // Probabilities of four consecutive steps are parked in shared memory (a column per stream, touched by
+          // this thread only) and leave as 96 contiguous bytes per stream: 3 full sectors instead of 4 x 24
+          // scattered bytes.
+          const int kq = (t_done - p.t0) & 3;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                lg[c] = part[c] + o[0][c] + o[1][c] + o[2][c] + p.fcb[c];
-                if (c < p.C) mx = fmaxf(mx, lg[c]);
-              }
-            }
-            float e[8], sum = 0.0f;
+          for (int c = 0; c < 6; ++c) sProb[(kq * 6 + c) * kTcTile + row] = e[c] * inv;
+          if (kq == 3 || t_done == t_end - 1) {
+            float4* dst = reinterpret_cast<float4*>(p.probs + (s * p.n + (t_done - kq)) * 6);
+            const int nq4 = ((kq + 1) * 6) >> 2;                 // whole float4s: 6 (4 steps), 4, 3, 1
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              e[c] = c < p.C ? ex2_approx((lg[c] - mx) * kLog2e) : 0.0f;    // 2 ulp: far inside the 1e-3 contract
-              sum += e[c];
-            }
-            const float inv = rcp_approx(sum);                              // sum in [1, C]
-            if (probs_batched) {
-              // Probabilities of four consecutive steps are parked in shared memory (a column per stream, touched by
-              // this thread only) and leave as 96 contiguous bytes per stream: 3 full sectors instead of 4 x 24
-              // scattered bytes.
-              const int kq = (t_done - p.t0) & 3;
-#pragma unroll
-              for (int c = 0; c < 6; ++c) sProb[(kq * 6 + c) * kTcTile + row] = e[c] * inv;
-              if (kq == 3 || t_done == t_end - 1) {
-                float4* dst = reinterpret_cast<float4*>(p.probs + (s * p.n + (t_done - kq)) * 6);
-                const int nq4 = ((kq + 1) * 6) >> 2;                 // whole float4s: 6 (4 steps), 4, 3, 1
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-                  if (i < nq4)
-                    dst[i] = make_float4(sProb[(4 * i) * kTcTile + row], sProb[(4 * i + 1) * kTcTile + row],
-                                         sProb[(4 * i + 2) * kTcTile + row], sProb[(4 * i + 3) * kTcTile + row]);
-                float* tail = reinterpret_cast<float*>(dst) + 4 * nq4;   // (kq+1)*6 mod 4 = 2 left over when kq is 0 or 2
-                if (((kq + 1) * 6) & 3) {
-                  tail[0] = sProb[(4 * nq4) * kTcTile + row];
-                  tail[1] = sProb[(4 * nq4 + 1) * kTcTile + row];
-                }
-              }
-            } else {
-              float* pr = p.probs + (s * p.n + t_done) * p.C;
-#pragma unroll
-              for (int c = 0; c < 8; ++c)
-                if (c < p.C) pr[c] = e[c] * inv;
-            }
-            if (p.logits) {
-              float* lo = p.logits + (s * p.n + t_done) * p.C;
-#pragma unroll
-              for (int c = 0; c < 8; ++c)
-                if (c < p.C) lo[c] = lg[c];
+            for (int i = 0; i < 6; ++i)
+              if (i < nq4)
+                dst[i] = make_float4(sProb[(4 * i) * kTcTile + row], sProb[(4 * i + 1) * kTcTile + row],
+                                     sProb[(4 * i + 2) * kTcTile + row], sProb[(4 * i + 3) * kTcTile + row]);
+            float* tail = reinterpret_cast<float*>(dst) + 4 * nq4;   // (kq+1)*6 mod 4 = 2 left over when kq is 0 or 2
+            if (((kq + 1) * 6) & 3) {
+              tail[0] = sProb[(4 * nq4) * kTcTile + row];
+              tail[1] = sProb[(4 * nq4 + 1) * kTcTile + row];
             }
           }
-          if (tl2) g_tc_timeline[256 + t_done * 4 + 2] = clock64();
+        } else {
+          float* pr = p.probs + (s * p.n + t_done) * p.C;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < p.C) pr[c] = e[c] * inv;
+        }
+        if (p.logits) {
+          float* lo = p.logits + (s * p.n + t_done) * p.C;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < p.C) lo[c] = lg[c];
         }
       };
+      bool emit_prev = false;                                      // whether the previous step was inside its stream's length
 
       // ---- prologue: A_h <- fp16(h).  All MMAs of the previous tile have completed (its last commit was waited
       // for by every thread), so the operand region is free.
@@ -564,6 +576,11 @@ gru_tc_kernel(const GruTcParams p) {
           }
         }
         if (tl) g_tc_timeline[t * 8 + 2] = clock64();
+        const bool have_logits = kLast && t > p.t0;                // the previous step's, issued behind this step's r gate
+        if (have_logits) {
+          if (ublk == 0) read_logits(nf & 1, emit_prev);
+          ++nf;
+        }
         mbar_acquire(&bars[kBarU], par);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -573,6 +590,7 @@ gru_tc_kernel(const GruTcParams p) {
         }
         tmem_publish(&bars[kBarARH]);
         if (tl) g_tc_timeline[t * 8 + 3] = clock64();
+        if (have_logits && ublk == 0) emit_probs(t - 1);
         // ---- u gate (beside the candidate MMAs): read once, kept in registers until the update
         float u[kTcUnits];
 #pragma unroll
@@ -603,15 +621,20 @@ gru_tc_kernel(const GruTcParams p) {
         mbar_acquire(&bars[kBarC], par);
         if (tl) g_tc_timeline[t * 8 + 5] = clock64();
         const bool live = t < len;
+        // (last layer: 8 units per pass -- with the lo halves of h' the 16-unit pass does not fit the 112 registers, and a
+        // spilled loop scalar costs an L2 round trip here: the L1 is 28 KB next to 227 KB of shared memory)
+        constexpr int kCw = kLast ? 8 : 16;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t vc[16];
-          tc::ld16(tmem + lane_sel + colDc + u0 + 16 * c, vc);
+        for (int c = 0; c < kTcUnits / kCw; ++c) {
+          uint32_t vc[kCw];
+          if constexpr (kCw == 16) tc::ld16(tmem + lane_sel + colDc + u0 + kCw * c, vc);
+          else tc::ld8(tmem + lane_sel + colDc + u0 + kCw * c, vc);
           tc::wait_ld();
-          uint32_t packed[8];
+          uint32_t packed[kCw / 2];
+          uint32_t packed_lo[kLast ? kCw / 2 : 1];
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const int j = 16 * c + i;
+          for (int i = 0; i < kCw; i += 4) {
+            const int j = kCw * c + i;
             const float4 pb = *reinterpret_cast<const float4*>(bC + j);
             float2 c01, c23;
             tanh4_pre(u2f2(vc[i], vc[i + 1]), u2f2(vc[i + 2], vc[i + 3]), make_float2(pb.x, pb.y), make_float2(pb.z, pb.w), c01, c23);
@@ -627,12 +650,33 @@ gru_tc_kernel(const GruTcParams p) {
             h[j + 1] = n01.y;
             h[j + 2] = n23.x;
             h[j + 3] = n23.y;
-            packed[i / 2] = tc::pack_half2(n01.x, n01.y);
-            packed[i / 2 + 1] = tc::pack_half2(n23.x, n23.y);
+            const __half2 p01 = __floats2half2_rn(n01.x, n01.y), p23 = __floats2half2_rn(n23.x, n23.y);
+            packed[i / 2] = *reinterpret_cast<const uint32_t*>(&p01);
+            packed[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&p23);
+#ifdef KWS_ABL_NOLO
+            if (false) {
+#else
+            if (kLast) {                                           // what the rounding lost: the FC's second operand
+#endif
+              const float2 b01 = __half22float2(p01), b23 = __half22float2(p23);
+              packed_lo[kLast ? i / 2 : 0] = tc::pack_half2(n01.x - b01.x, n01.y - b01.y);
+              packed_lo[kLast ? i / 2 + 1 : 0] = tc::pack_half2(n23.x - b23.x, n23.y - b23.y);
+            }
           }
-          if (more) tc::st8(my_ah + 8 * c, packed);
+          if constexpr (kLast) {
+            const uint32_t vhi[4] = {packed[0], packed[1], packed[2], packed[3]};
+            const uint32_t vlo[4] = {packed_lo[0], packed_lo[kLast ? 1 : 0], packed_lo[kLast ? 2 : 0], packed_lo[kLast ? 3 : 0]};
+            tc::st4(my_ah + 4 * c, vhi);
+            tc::st4(my_alo + 4 * c, vlo);
+          } else {
+            if (more) {
+              const uint32_t vhi[8] = {packed[0], packed[1], packed[2], packed[3], packed[kLast ? 0 : 4], packed[kLast ? 0 : 5],
+                                       packed[kLast ? 0 : 6], packed[kLast ? 0 : 7]};
+              tc::st8(my_ah + 8 * c, vhi);
+            }
+          }
         }
-        if (more) tmem_publish(&bars[kBarAH]);                     // releases the next step's r/u MMAs
+        if (kLast || more) tmem_publish(&bars[kBarAH]);            // releases the next step's r/u MMAs (last layer: and this step's FC)
         if (tl) g_tc_timeline[t * 8 + 6] = clock64();
         // ---- outputs of this step, in the shadow of the next step's r-gate MMAs.  dynamic_rnn: zero output past the length
         const bool emit = all_live || live;
@@ -648,9 +692,18 @@ gru_tc_kernel(const GruTcParams p) {
             v.w = emit ? tc::pack_half2(h[8 * q + 6], h[8 * q + 7]) : 0u;
             dst[q * kTcTile] = v;
           }
-        } else {
-          fc_finish(t, emit);
         }
+        emit_prev = emit;
+      }
+      if (kLast && p.nt > 0) {
+        // the tile's last logits; every thread waits for that product because the next tile's prologue overwrites A_h
+        if (ublk == 0) {
+          read_logits(nf & 1, emit_prev);
+          emit_probs(t_end - 1);
+        } else {
+          mbar_acquire(&bars[kBarF], nf & 1);
+        }
+        ++nf;
       }
       if (p.timeline && blockIdx.x == 0 && tid == 0 && tile == blockIdx.x) g_tc_timeline[7] = clock64();
       if (ok) {
@@ -667,7 +720,7 @@ gru_tc_kernel(const GruTcParams p) {
 
 static size_t gru_tc_smem_bytes(int kxw, bool last, int nbuf) {
   return static_cast<size_t>(768) * (kxw + kHidden) + static_cast<size_t>(nbuf) * (kxw / 8) * tc::kTileChunkBytes +
-         sizeof(float) * 384 + (last ? sizeof(float) * (3 * kTcTile * 8 + kHidden * kTcMaxClasses + 4 * 6 * kTcTile) : 0) +
+         sizeof(float) * 384 + (last ? kFcOperandBytes + sizeof(float) * (4 * 6 + kTcMaxClasses) * kTcTile : 0) +
          kNumBars * sizeof(uint64_t) + 16;
 }
 static size_t max_dynamic_smem(int device) {

@@ -232,7 +232,7 @@ def load_peaks():
 def load_traffic(S):
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
     capture, scaled from the captured stream count to S; None when the capture file is absent."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(path):
         return {}
     d = json.load(open(path))
@@ -638,8 +638,8 @@ def run_ours(args, rank, world, local_rank):
     kname = "gru_tc_kernel" if args.precision == "tc" else "gru_layer_kernel"
     traffic = load_traffic(S) if args.precision == "tc" else {}
     gru_traffic = None
-    if "gru_tc_kernel<0,1>" in traffic:
-        gru_traffic = 0.5 * (traffic["gru_tc_kernel<0,1>"] + traffic["gru_tc_kernel<1,0>"])   # mean of the two launches
+    if "gru_tc_kernel_layer0" in traffic:
+        gru_traffic = 0.5 * (traffic["gru_tc_kernel_layer0"] + traffic["gru_tc_kernel_layer1"])   # mean of the two launches
     roof_gru = dict(kernel=kname, bound="tensor", achieved=achieved_tf, peak=peaks["bf16_sustained"],
                     unit="TFLOP/s", frac=achieved_tf / peaks["bf16_sustained"], frac_of_burst_peak=achieved_tf / peaks["bf16"],
                     traffic=gru_traffic, launch_ms=gru_launch_ms,

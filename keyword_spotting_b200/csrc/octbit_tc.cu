@@ -288,7 +288,11 @@ octbit_tc_kernel(const __grid_constant__ CUtensorMap tmap, const OctbitTcParams 
         tc::ld16(tmem + lane_sel + 256 * buf + c0, v);
         tc::wait_ld();
         if (row_qmax * sAny[ch] >= 32768) {                               // rare: a near-extreme code x a chunk with heavy pairs
-#pragma unroll
+          // kept OUT of the unrolled code (one compact loop, its 16 corrections parked in this lane's row of the staging
+          // tile): unrolled sixteen times it set the register allocation of the whole role and spilled the store
+          // loop's addresses -- a spill reload is an L2 round trip next to 200 KB of shared memory
+          int* dpark = reinterpret_cast<int*>(stage + lane * 20);
+#pragma unroll 1
           for (int i = 0; i < 16; ++i) {
             const int n = c0 + i;
             const int cnt = sCnt[n];
@@ -312,7 +316,15 @@ octbit_tc_kernel(const __grid_constant__ CUtensorMap tmap, const OctbitTcParams 
                 delta += sat16(pq) - pq;
               }
             }
-            v[i] += static_cast<uint32_t>(delta);
+            dpark[i] = delta;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const int4 d4 = *reinterpret_cast<const int4*>(dpark + i);
+            v[i] += static_cast<uint32_t>(d4.x);
+            v[i + 1] += static_cast<uint32_t>(d4.y);
+            v[i + 2] += static_cast<uint32_t>(d4.z);
+            v[i + 3] += static_cast<uint32_t>(d4.w);
           }
         }
         // the four fp32 lane sums of the reference are exact integers below 2^24 (K <= 512), so their lane-ordered

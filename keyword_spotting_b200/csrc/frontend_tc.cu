@@ -212,9 +212,13 @@ frontend_tc_kernel(const FrontendTcParams p) {
   auto item_of = [&](long i) -> long { return blockIdx.x + i * static_cast<long>(gridDim.x); };
   auto stream_of = [&](long item) -> long { return p.groups == 1 ? item : item / p.groups; };
 
-  // (no setmaxnreg: every role fits the registers an 896-thread CTA gets; the pool of a CTA is what it was launched
-  // with, so the 16 combination warps could only grow if the other 12 shrank by as much)
+  // Registers: 1024 threads are launched at 64 each, the combination role needs ~76 (at 64 it spilled a dozen values per
+  // item, and a spill reload is an L2 round trip next to 170 KB of shared memory).  setmaxnreg moves 16 registers per
+  // thread from warpgroups 4-7 (issuer, loaders, mel) to warpgroups 0-3; the instruction is warpgroup-wide and the pool
+  // of a CTA is what it was launched with, so the two sides must balance exactly: 512 x (+16) = 512 x (-16).
+  // (one instruction at the head of every role's branch: the compiler budgets a region by the setmaxnreg that dominates it)
   if (warp == kFtMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     // ================================================================ MMA issuer
     const bool lead = lane == 0;
     const uint64_t b1desc = tc::smem_desc(tc::smem_u32(sB1), kFtB1Lbo, kFtB1Sbo);
@@ -265,6 +269,7 @@ frontend_tc_kernel(const FrontendTcParams p) {
     }
   } else if (warp >= kFtLoadWarp0 && warp < kFtOutWarp0) {
     // ================================================================ PCM loaders: int16 -> (x_hi, x_lo) fp16 operands
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     const int ltid = tid - 32 * kFtLoadWarp0;
     for (long i = 0; i < n_mine; ++i) {
       const long item = item_of(i);
@@ -384,6 +389,7 @@ frontend_tc_kernel(const FrontendTcParams p) {
     }
   } else if (warp >= kFtOutWarp0) {
     // ================================================================ mel projection + output: lane = frame
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     const int otid = tid - 32 * kFtOutWarp0;
     const int q = warp - kFtOutWarp0;
     for (long i = 0; i < n_mine; ++i) {
@@ -467,6 +473,7 @@ frontend_tc_kernel(const FrontendTcParams p) {
     }
   } else {
     // ================================================================ combination: lane k (and 200 - k) x 8 frames
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     const int q = warp & 3, F = warp >> 2;
     const int k = 32 * q + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(32 * q) << 16;

@@ -220,25 +220,28 @@ frontend_tc_kernel(const FrontendTcParams p) {
   if (warp == kFtMmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     // ================================================================ MMA issuer
-    const bool lead = lane == 0;
     const uint64_t b1desc = tc::smem_desc(tc::smem_u32(sB1), kFtB1Lbo, kFtB1Sbo);
     // an item's block transforms: Re tile, then Im tile.  The issuing warp shares its scheduler with seven others and
     // a tcgen05.mma holds the issue slot ~60 cycles: fully unrolled, every operand address in uniform registers.
     const uint32_t idesc = tc::idesc_f16(128, 128);
-    auto gemm1 = [&](uint64_t bH, uint64_t bL) {
+    // (issued from one elect.sync region: back-to-back UTCHMMA -- under a `lane == 0` predicate ptxas wraps every MMA in
+    // a six-instruction loop over the active lanes)
+    auto gemm1 = [&](uint64_t bH, uint64_t bL, uint64_t* bar_d, uint64_t* bar_b) {
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        const uint32_t d = tmem + kFtColD + 128 * tile;
-        const uint32_t a_hi = tmem + kFtColA + 40 * (2 * tile), a_lo = a_hi + 40;
+        for (int tile = 0; tile < 2; ++tile) {
+          const uint32_t d = tmem + kFtColD + 128 * tile;
+          const uint32_t a_hi = tmem + kFtColA + 40 * (2 * tile), a_lo = a_hi + 40;
 #pragma unroll
-        for (int k16 = 0; k16 < kFtBlk / 16; ++k16) {
-          const uint64_t step = static_cast<uint64_t>(k16 * ((2 * kFtB1Lbo) >> 4));
-          if (lead) {
+          for (int k16 = 0; k16 < kFtBlk / 16; ++k16) {
+            const uint64_t step = static_cast<uint64_t>(k16 * ((2 * kFtB1Lbo) >> 4));
             tc::mma_ts(d, a_hi + 8 * k16, bH + step, idesc, k16 > 0);
             tc::mma_ts(d, a_hi + 8 * k16, bL + step, idesc, true);
             tc::mma_ts(d, a_lo + 8 * k16, bH + step, idesc, true);
           }
         }
+        tc::commit(bar_d);
+        tc::commit(bar_b);
       }
     };
     for (long i = 0; i < n_mine; ++i) {
@@ -252,19 +255,8 @@ frontend_tc_kernel(const FrontendTcParams p) {
       // (the buffer index is loop-carried, which the compiler cannot prove warp-uniform: branch on it so that every
       // descriptor inside is derived from kernel constants and stays in uniform registers -- no per-MMA broadcast loop)
       constexpr uint64_t kPart = static_cast<uint64_t>(kFtB1Part >> 4);
-      if (buf == 0) {
-        gemm1(b1desc, b1desc + kPart);
-        if (lead) {
-          tc::commit(&bars[kFbDfull]);
-          tc::commit(&bars[kFbBempty0]);
-        }
-      } else {
-        gemm1(b1desc + 2 * kPart, b1desc + 3 * kPart);
-        if (lead) {
-          tc::commit(&bars[kFbDfull]);
-          tc::commit(&bars[kFbBempty1]);
-        }
-      }
+      if (buf == 0) gemm1(b1desc, b1desc + kPart, &bars[kFbDfull], &bars[kFbBempty0]);
+      else gemm1(b1desc + 2 * kPart, b1desc + 3 * kPart, &bars[kFbDfull], &bars[kFbBempty1]);
       FT_TIME(0, 2);
     }
   } else if (warp >= kFtLoadWarp0 && warp < kFtOutWarp0) {

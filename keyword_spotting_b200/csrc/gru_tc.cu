@@ -243,14 +243,13 @@ gru_tc_kernel(const GruTcParams p) {
     // (setmaxnreg is a warpgroup-wide instruction: warps 16-19 must all execute the same one)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == kMmaWarp) {
-    const bool lead = lane == 0;
     const int nx = kNX ? kNX : p.kx / 16;
     const bool split = kNX ? kNX == 3 : p.kxw != p.kx;             // 3-term x product
     const bool two = p.nbuf == 2;
     const uint32_t sbo = static_cast<uint32_t>(ktot / 8) * 128;
     const uint32_t idesc128 = tc::idesc_f16(128, 128);
-    // All operand addresses are computed warp-uniformly (they live in uniform registers); only the MMA itself is
-    // predicated on the elected lane.  B descriptor of K-chunk k16 for the weight rows starting at row0 =
+    // All operand addresses are computed warp-uniformly (they live in uniform registers); the MMAs of a group are issued
+    // from ONE elect.sync region (tc::elect_one): back-to-back UTCHMMA, no per-instruction lane loop.  B descriptor of K-chunk k16 for the weight rows starting at row0 =
     // base + ((row0/8)*sbo + 256*k16)/16 added to the 14-bit start-address field (shared memory < 256 KB: no carry).
     const uint64_t wbase = tc::smem_desc(tc::smem_u32(sW), 128, sbo);
     const uint32_t row_step = (16 * sbo) >> 4;                             // 128 output rows
@@ -267,16 +266,18 @@ gru_tc_kernel(const GruTcParams p) {
     auto issue_x_from = [&](uint64_t xdesc, uint32_t dcol, int rblk) {
       const uint64_t wrow = wb + rblk * row_step;
       const uint64_t xlo = xdesc + static_cast<uint64_t>(nx) * kStepA;    // the lo chunks follow the hi chunks
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                     // x_hi * Wx_hi
-        if (lead) tc::mma_ss(tm + dcol, xdesc + k16 * kStepA, wrow + 16 * k16, idesc128, k16 > 0);
-      if (split) {
+        for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                   // x_hi * Wx_hi
+          tc::mma_ss(tm + dcol, xdesc + k16 * kStepA, wrow + 16 * k16, idesc128, k16 > 0);
+        if (split) {
 #pragma unroll
-        for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                   // x_lo * Wx_hi
-          if (lead) tc::mma_ss(tm + dcol, xlo + k16 * kStepA, wrow + 16 * k16, idesc128, true);
+          for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                 // x_lo * Wx_hi
+            tc::mma_ss(tm + dcol, xlo + k16 * kStepA, wrow + 16 * k16, idesc128, true);
 #pragma unroll
-        for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                   // x_hi * Wx_lo
-          if (lead) tc::mma_ss(tm + dcol, xdesc + k16 * kStepA, wrow + 16 * (nx + k16), idesc128, true);
+          for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)                 // x_hi * Wx_lo
+            tc::mma_ss(tm + dcol, xdesc + k16 * kStepA, wrow + 16 * (nx + k16), idesc128, true);
+        }
       }
     };
     // (the buffer index is loop-carried, which the compiler cannot prove warp-uniform: branch on it so that every
@@ -284,9 +285,11 @@ gru_tc_kernel(const GruTcParams p) {
     auto issue_x = [&](int buf, uint32_t dcol, int rblk) {
       if (!kXSmem) {                                                       // x in TMEM (never split: a layer's outputs are in [-1, 1])
         const uint64_t wrow = wb + rblk * row_step;
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)
-          if (lead) tc::mma_ts(tm + dcol, tm + colAx + 8 * k16, wrow + 16 * k16, idesc128, k16 > 0);
+          for (int k16 = 0; k16 < (kNX ? kNX : nx); ++k16)
+            tc::mma_ts(tm + dcol, tm + colAx + 8 * k16, wrow + 16 * k16, idesc128, k16 > 0);
+        }
       } else if (buf == 0) {
         issue_x_from(xd0, dcol, rblk);
       } else {
@@ -296,12 +299,14 @@ gru_tc_kernel(const GruTcParams p) {
     const int nxw = p.kxw / 16;
     auto issue_h = [&](uint32_t dcol, int rblk) {                          // += A_h * Wh[128*rblk .. +127]
       const uint64_t wrow = wb + rblk * row_step + 16 * nxw;
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int k16 = 0; k16 < kHidden / 16; ++k16)
-        if (lead) tc::mma_ts(tm + dcol, tm + colAh + 8 * k16, wrow + 16 * k16, idesc128, true);
+        for (int k16 = 0; k16 < kHidden / 16; ++k16)
+          tc::mma_ts(tm + dcol, tm + colAh + 8 * k16, wrow + 16 * k16, idesc128, true);
+      }
     };
     auto prefetch = [&](long tile, int t, int buf) {                       // x of (tile, t) -> buffer `buf`
-      if (lead) {
+      if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(&bars[kBarXF0 + buf], xbytes);
         tc::bulk_g2s(sX + static_cast<size_t>(buf) * xbytes, p.x_tiles + (tile * p.n + t) * static_cast<long>(xbytes), xbytes,
                      &bars[kBarXF0 + buf]);
@@ -316,15 +321,14 @@ gru_tc_kernel(const GruTcParams p) {
     const uint64_t fdesc = tc::smem_desc(tc::smem_u32(sWfc), 128, (kHidden / 8) * 128);
     uint64_t fd = fdesc;
     auto issue_fc = [&]() {
-#ifndef KWS_ABL_NOFCMMA
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int j = 0; j < kHidden / 16; ++j)
-        if (lead) tc::mma_ts(tm + colDc, tm + colAh + 8 * j, fd + 16 * j, idesc16, j > 0);
+        for (int j = 0; j < kHidden / 16; ++j) tc::mma_ts(tm + colDc, tm + colAh + 8 * j, fd + 16 * j, idesc16, j > 0);
 #pragma unroll
-      for (int j = 0; j < kHidden / 16; ++j)
-        if (lead) tc::mma_ts(tm + colDc, tm + colDu + 32 * (j >> 1) + 8 * (j & 1), fd + 16 * j, idesc16, true);
-#endif
-      if (lead) tc::commit(&bars[kBarF]);
+        for (int j = 0; j < kHidden / 16; ++j)
+          tc::mma_ts(tm + colDc, tm + colDu + 32 * (j >> 1) + 8 * (j & 1), fd + 16 * j, idesc16, true);
+        tc::commit(&bars[kBarF]);
+      }
     };
     uint32_t it = 0;                                                       // (tile, step) pairs done by this CTA
     uint32_t ah = 0, nf = 0;                                               // A_h hand-overs consumed, FC products issued
@@ -349,25 +353,25 @@ gru_tc_kernel(const GruTcParams p) {
         mbar_acquire(&bars[kBarAH], ah & 1);                               // h_{t-1} in A_h; every MMA of the previous step is complete
         ++ah;
         issue_h(colDr, 0);
-        if (lead) tc::commit(&bars[kBarR]);
+        if (tc::elect_one()) tc::commit(&bars[kBarR]);
         if (kLast && t > p.t0) {                                           // logits of the previous step, behind the critical r gate
           issue_fc();
           ++nf;
         }
         if (kXSmem && two && has_next) prefetch(ntile, nt1, buf ^ 1);      // the other buffer's last readers were the previous step's MMAs
 #ifdef KWS_L2_PREFETCH
-        if (!kXSmem && lead && t + KWS_L2_PREFETCH < t_end)                // the gate threads' x loads of a later step: HBM -> L2 now
+        if (!kXSmem && t + KWS_L2_PREFETCH < t_end && tc::elect_one())                // the gate threads' x loads of a later step: HBM -> L2 now
           tc::bulk_prefetch_l2(p.x_f16 + (tile * p.n + t + KWS_L2_PREFETCH) * static_cast<long>(16 * kTcTile * 8), 16 * tc::kTileChunkBytes);
 #endif
         issue_x(buf, colDu, 1);                                            // u gate
         issue_h(colDu, 1);
-        if (lead) tc::commit(&bars[kBarU]);
+        if (tc::elect_one()) tc::commit(&bars[kBarU]);
         if (kLast && nf > 0) mbar_acquire(&bars[kBarFR], (nf - 1) & 1);    // the logits have left the candidate columns
         issue_x(buf, colDc, 2);                                            // candidate, x-part
-        if (!kXSmem && lead) tc::commit(&bars[kBarXD]);                    // A_x has been read: the gate threads may store x_{t+1}
+        if (!kXSmem && tc::elect_one()) tc::commit(&bars[kBarXD]);                    // A_x has been read: the gate threads may store x_{t+1}
         mbar_acquire(&bars[kBarARH], par);                                 // r*h in A_h (and D_r read by every gate thread)
         issue_h(colDc, 2);
-        if (lead) tc::commit(&bars[kBarC]);
+        if (tc::elect_one()) tc::commit(&bars[kBarC]);
         if (kLast && !step_next) {                                         // the tile's last step: its logits are not followed by an r gate
           mbar_acquire(&bars[kBarAH], ah & 1);
           ++ah;

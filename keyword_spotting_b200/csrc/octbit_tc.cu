@@ -186,7 +186,7 @@ octbit_tc_kernel(const __grid_constant__ CUtensorMap tmap, const OctbitTcParams 
 
   if (warp == kOtTmaWarp) {
     // ================================================= TMA: x [A, K] fp32 -> ring of [16, K] slabs
-    if (lane == 0) {
+    if (tc::elect_one()) {
       uint32_t n = 0;
       for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         for (int c = 0; c < kChunks; ++c, ++n) {
@@ -251,7 +251,7 @@ octbit_tc_kernel(const __grid_constant__ CUtensorMap tmap, const OctbitTcParams 
       const int buf = it & 1;
       tc::mbar_wait(&bars[kOtFull0 + buf], (it >> 1) & 1);
       tc::fence_after_sync();
-      if (lane == 0) {
+      if (tc::elect_one()) {                                              // one elect.sync region: straight UTCIMMA issue
         const uint64_t ad = buf ? adesc1 : adesc0;
 #pragma unroll 1
         for (int k32 = 0; k32 < K / 32; ++k32)                            // two K-adjacent core matrices per MMA

@@ -109,6 +109,22 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
 // descriptor SBO is then the stride between 8-groups of N and LBO the stride between 8-groups of K)
 __host__ __device__ constexpr uint32_t idesc_f16_bmn(int M, int N) { return idesc_f16(M, N) | (1u << 16); }
 
+// One lane of a CONVERGED warp (elect.sync).  Guard tcgen05.mma / commit / bulk-copy issue with this, not with
+// `lane == 0`: ptxas recognises the elected region as single-threaded and emits the uniform-datapath instruction
+// as is, whereas under an ordinary lane predicate it wraps EVERY such instruction in a loop over the active lanes
+// (ELECT, two PLOP3, BRA.U.ANY: six instructions and a branch per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA (issued by ONE thread).  D[tmem] (+)= A[tmem] * B[smem]^T
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
   asm volatile(

@@ -11,9 +11,9 @@
 // tf.contrib.layers.layer_norm of that TensorFlow era normalises over all non-batch axes of [B, T', N]
 // (one mean/variance per utterance), gamma/beta per channel, epsilon 1e-12.
 //
-// First correct version: fp32 FFMA kernels (smem-tiled GEMM, one-thread-per-query online-softmax attention with
-// K/V blocks staged in shared memory, per-utterance fused add + layer-norm).  The work is 0.7 GFLOP per 8 s
-// utterance; moving the dense layers to tcgen05 is listed in DESIGN.md.
+// Dense layers: tcgen05 with fp16 hi/lo operand splits, fp32-grade (attention_tc.cu); the fp32 FFMA GEMM below remains for
+// shapes that kernel does not take.  Attention itself: one thread per query, online softmax, K/V blocks staged in shared
+// memory (fp32 FFMA); per-utterance fused add + layer-norm.  The work is 0.7 GFLOP per 8 s utterance.
 #include <cmath>
 #include <vector>
 
@@ -27,6 +27,11 @@ struct kws_attention {
     float *w_qkv = nullptr, *b_qkv = nullptr, *ln1_g = nullptr, *ln1_b = nullptr;
     float *w_ff1 = nullptr, *b_ff1 = nullptr, *w_ff2 = nullptr, *b_ff2 = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   } layer[8];
+  // the dense layers' weights as pre-split fp16 tensor-core operands (attention_tc.cu); null -> the FFMA kernel
+  struct Packed {
+    unsigned char* w = nullptr;
+    int nchunks = 0;
+  } p_in, p_qkv[8], p_ff1[8], p_ff2[8];
   float* pe = nullptr;          // [pe_rows, N] from the K6 kernel
   int pe_rows = 0;
   float* scratch = nullptr;     // xin | x | y | att | big
@@ -34,6 +39,11 @@ struct kws_attention {
 };
 
 namespace kws {
+
+bool att_linear_tc_supported(int K, int N);                                                   // attention_tc.cu
+int att_pack_linear(const float* W, int K, int N, unsigned char** out, int* nchunks_out);
+int launch_att_linear_tc(const float* A, const unsigned char* wpack, int nchunks, const float* bias, const float* pe, int Tp,
+                         long rows, int K, int N, bool relu, bool add_pe, float* Y, cudaStream_t st);
 
 constexpr int kAttHidden = 128;
 constexpr int kAttHeadDim = 16;
@@ -254,14 +264,21 @@ static void att_free(kws_attention* m) {
     cudaFree(l.w_qkv); cudaFree(l.b_qkv); cudaFree(l.ln1_g); cudaFree(l.ln1_b); cudaFree(l.w_ff1);
     cudaFree(l.b_ff1); cudaFree(l.w_ff2); cudaFree(l.b_ff2); cudaFree(l.ln2_g); cudaFree(l.ln2_b);
   }
+  cudaFree(m->p_in.w);
+  for (int l = 0; l < 8; ++l) {
+    cudaFree(m->p_qkv[l].w);
+    cudaFree(m->p_ff1[l].w);
+    cudaFree(m->p_ff2[l].w);
+  }
   cudaFree(m->pe);
   cudaFree(m->scratch);
   delete m;
 }
 
 template <bool R, bool P>
-static int att_linear(const float* A, const float* W, const float* bias, const float* pe, int Tp, long rows, int K, int N,
-                      float* Y, cudaStream_t st) {
+static int att_linear(const float* A, const float* W, const kws_attention::Packed& pk, const float* bias, const float* pe, int Tp,
+                      long rows, int K, int N, float* Y, cudaStream_t st) {
+  if (pk.w) return launch_att_linear_tc(A, pk.w, pk.nchunks, bias, pe, Tp, rows, K, N, R, P, Y, st);   // tcgen05, fp32-grade
   dim3 grid(static_cast<unsigned>(ceil_div(rows, 64)), static_cast<unsigned>(ceil_div(N, 64)));
   att_linear_kernel<R, P><<<grid, 256, 0, st>>>(A, W, bias, pe, Tp, rows, K, N, Y);
   KWS_LAUNCH_OK("att_linear_kernel");
@@ -313,7 +330,11 @@ extern "C" int kws_attention_create(const kws_attention_config* cfg, const kws_a
     if (rc == KWS_OK) rc = att_upload(&L.b_ff2, w->b_ff2[l], N);
     if (rc == KWS_OK) rc = att_upload(&L.ln2_g, w->ln2_g[l], N);
     if (rc == KWS_OK) rc = att_upload(&L.ln2_b, w->ln2_b[l], N);
+    if (rc == KWS_OK && att_linear_tc_supported(N, 3 * N)) rc = att_pack_linear(w->w_qkv[l], N, 3 * N, &m->p_qkv[l].w, &m->p_qkv[l].nchunks);
+    if (rc == KWS_OK && att_linear_tc_supported(N, F)) rc = att_pack_linear(w->w_ff1[l], N, F, &m->p_ff1[l].w, &m->p_ff1[l].nchunks);
+    if (rc == KWS_OK && att_linear_tc_supported(F, N)) rc = att_pack_linear(w->w_ff2[l], F, N, &m->p_ff2[l].w, &m->p_ff2[l].nchunks);
   }
+  if (rc == KWS_OK && att_linear_tc_supported(Kin, N)) rc = att_pack_linear(w->w_in, Kin, N, &m->p_in.w, &m->p_in.nchunks);
   if (rc == KWS_OK) rc = att_upload(&m->w_out, w->w_out, static_cast<size_t>(N) * C);
   if (rc == KWS_OK) rc = att_upload(&m->b_out, w->b_out, C);
   if (rc != KWS_OK) {
@@ -382,18 +403,18 @@ extern "C" int kws_attention_forward(kws_attention* m, const float* mel, int64_t
   const long total_in = rows * Kin;
   att_combine_kernel<<<static_cast<unsigned>(ceil_div(total_in, 256)), 256, 0, st>>>(mel, B, T, c.n_mel, c.combine_frame, Tp, xin);
   KWS_LAUNCH_OK("att_combine_kernel");
-  int rc = att_linear<false, true>(xin, m->w_in, m->b_in, m->pe, Tp, rows, Kin, N, x, st);
+  int rc = att_linear<false, true>(xin, m->w_in, m->p_in, m->b_in, m->pe, Tp, rows, Kin, N, x, st);
   for (int l = 0; l < c.num_layers && rc == KWS_OK; ++l) {
     const auto& L = m->layer[l];
-    rc = att_linear<false, false>(x, L.w_qkv, L.b_qkv, nullptr, Tp, rows, N, 3 * N, big, st);
+    rc = att_linear<false, false>(x, L.w_qkv, m->p_qkv[l], L.b_qkv, nullptr, Tp, rows, N, 3 * N, big, st);
     if (rc != KWS_OK) break;
     dim3 ga(static_cast<unsigned>(ceil_div(Tp, 128)), static_cast<unsigned>(c.heads), static_cast<unsigned>(B));
     att_attention_kernel<<<ga, 128, 0, st>>>(big, Tp, c.heads, att);
     KWS_LAUNCH_OK("att_attention_kernel");
     att_add_layernorm_kernel<<<static_cast<unsigned>(B), 1024, 0, st>>>(att, x, L.ln1_g, L.ln1_b, Tp, N, y);
     KWS_LAUNCH_OK("att_add_layernorm_kernel");
-    rc = att_linear<true, false>(y, L.w_ff1, L.b_ff1, nullptr, Tp, rows, N, F, big, st);
-    if (rc == KWS_OK) rc = att_linear<false, false>(big, L.w_ff2, L.b_ff2, nullptr, Tp, rows, F, N, att, st);
+    rc = att_linear<true, false>(y, L.w_ff1, m->p_ff1[l], L.b_ff1, nullptr, Tp, rows, N, F, big, st);
+    if (rc == KWS_OK) rc = att_linear<false, false>(big, L.w_ff2, m->p_ff2[l], L.b_ff2, nullptr, Tp, rows, F, N, att, st);
     if (rc != KWS_OK) break;
     att_add_layernorm_kernel<<<static_cast<unsigned>(B), 1024, 0, st>>>(att, y, L.ln2_g, L.ln2_b, Tp, N, x);
     KWS_LAUNCH_OK("att_add_layernorm_kernel");

@@ -44,6 +44,8 @@ bool att_linear_tc_supported(int K, int N);                                     
 int att_pack_linear(const float* W, int K, int N, unsigned char** out, int* nchunks_out);
 int launch_att_linear_tc(const float* A, const unsigned char* wpack, int nchunks, const float* bias, const float* pe, int Tp,
                          long rows, int K, int N, bool relu, bool add_pe, float* Y, cudaStream_t st);
+bool att_core_tc_supported(int Tp, int heads, int hidden);
+int launch_att_core_tc(const float* qkv, long B, int Tp, int heads, float* out, cudaStream_t st);
 
 constexpr int kAttHidden = 128;
 constexpr int kAttHeadDim = 16;
@@ -408,9 +410,14 @@ extern "C" int kws_attention_forward(kws_attention* m, const float* mel, int64_t
     const auto& L = m->layer[l];
     rc = att_linear<false, false>(x, L.w_qkv, m->p_qkv[l], L.b_qkv, nullptr, Tp, rows, N, 3 * N, big, st);
     if (rc != KWS_OK) break;
-    dim3 ga(static_cast<unsigned>(ceil_div(Tp, 128)), static_cast<unsigned>(c.heads), static_cast<unsigned>(B));
-    att_attention_kernel<<<ga, 128, 0, st>>>(big, Tp, c.heads, att);
-    KWS_LAUNCH_OK("att_attention_kernel");
+    if (att_core_tc_supported(Tp, c.heads, N)) {                     // tcgen05: T' <= 400 keys
+      rc = launch_att_core_tc(big, B, Tp, c.heads, att, st);
+      if (rc != KWS_OK) break;
+    } else {
+      dim3 ga(static_cast<unsigned>(ceil_div(Tp, 128)), static_cast<unsigned>(c.heads), static_cast<unsigned>(B));
+      att_attention_kernel<<<ga, 128, 0, st>>>(big, Tp, c.heads, att);
+      KWS_LAUNCH_OK("att_attention_kernel");
+    }
     att_add_layernorm_kernel<<<static_cast<unsigned>(B), 1024, 0, st>>>(att, x, L.ln1_g, L.ln1_b, Tp, N, y);
     KWS_LAUNCH_OK("att_add_layernorm_kernel");
     rc = att_linear<true, false>(y, L.w_ff1, m->p_ff1[l], L.b_ff1, nullptr, Tp, rows, N, F, big, st);

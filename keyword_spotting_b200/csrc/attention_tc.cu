@@ -200,4 +200,227 @@ int launch_att_linear_tc(const float* A, const unsigned char* wpack, int nchunks
   return KWS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Multi-head attention core on the tensor cores (models/attention_ctc.py:28-58): per (utterance, head)
+//     O = softmax(Q K^T / sqrt(16)) V        over ALL T' keys (no mask), T' <= 400, head size 16.
+// One CTA per (utterance, head); K and V^T are split into fp16 hi/lo once and stay in shared memory as B operands, the
+// CTA then walks the utterance's query tiles of 128 rows:
+//   S = Q K^T   6 tcgen05.mma (3 hi/lo products x N = 256 + the rest, K = 16) into T' columns of TMEM;
+//   pass 1      every thread reads its row's scores (two warps per TMEM lane quarter, half of the keys each): row maximum;
+//   pass 2      re-read, p = 2^(s - max), row sum; p is written back IN PLACE as the next product's A operand: the 16 score
+//               columns of a key group become 8 columns of fp16(p) and 8 columns of its rounding remainder;
+//   O = P V     75 tcgen05.mma (3 products x 25 key groups, N = 16, TS form) into 16 more TMEM columns;
+//   O / sum -> HBM (64 bytes per query row).
+// fp32-grade throughout (the dropped lo x lo terms are 2^-22 relative): the model's 1e-4 parity tests are unchanged.
+constexpr int kAcThreads = 256;
+constexpr int kAcD = 16;
+constexpr int kAcMaxKeys = 400;                  // T' padded to a multiple of 16; TMEM: 400 score columns + 16 for O
+constexpr int kAcSboK = 2 * 128;                 // K operand [keys, 16]: two K-adjacent core matrices per 8-key group
+constexpr int kAcPartK = (kAcMaxKeys / 8) * kAcSboK;      // 12800
+constexpr int kAcSboV = (kAcMaxKeys / 8) * 128;  // V^T operand [16, keys]: 6400 between the two 8-row groups
+constexpr int kAcPartV = 2 * kAcSboV;            // 12800
+constexpr int kAcPartQ = (128 / 8) * kAcSboK;    // 4096
+constexpr int kAcColO = kAcMaxKeys;
+
+__global__ void __launch_bounds__(kAcThreads, 1)
+att_core_tc_kernel(const float* __restrict__ qkv, int Tp, int heads, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sK = smem;                                      // [hi | lo] x kAcPartK
+  unsigned char* sV = sK + 2 * kAcPartK;
+  unsigned char* sQ = sV + 2 * kAcPartV;
+  __shared__ float sMax[2][128], sSum[2][128];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = heads * kAcD;
+  const int h = blockIdx.x % heads;
+  const long b = blockIdx.x / heads;
+  const float* base = qkv + b * Tp * 3L * N + h * kAcD;
+  const int Kp = (Tp + 15) & ~15;                               // keys padded to whole MMA K steps
+  const int groups = Kp / 16;
+  const float scale = rsqrtf(static_cast<float>(kAcD)) * 1.4426950408889634f;     // 1/sqrt(d), in log2 units
+
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_fence_init();
+  }
+  // ---- K and V^T of this head, split into hi / lo fp16 (zero rows past T')
+  for (int j = tid; j < Kp; j += kAcThreads) {
+    float kf[16], vf[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
+      if (j < Tp) {
+        k4 = __ldg(reinterpret_cast<const float4*>(base + static_cast<long>(j) * 3 * N + N) + c);
+        v4 = __ldg(reinterpret_cast<const float4*>(base + static_cast<long>(j) * 3 * N + 2 * N) + c);
+      }
+      kf[4 * c] = k4.x; kf[4 * c + 1] = k4.y; kf[4 * c + 2] = k4.z; kf[4 * c + 3] = k4.w;
+      vf[4 * c] = v4.x; vf[4 * c + 1] = v4.y; vf[4 * c + 2] = v4.z; vf[4 * c + 3] = v4.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {                                // K: 8 consecutive d of key j are one 16-byte row piece
+      const float v8[8] = {kf[8 * c], kf[8 * c + 1], kf[8 * c + 2], kf[8 * c + 3], kf[8 * c + 4], kf[8 * c + 5], kf[8 * c + 6], kf[8 * c + 7]};
+      uint4 hi, lo;
+      tc::split_half8(v8, &hi, &lo);
+      const uint32_t off = (j >> 3) * kAcSboK + c * 128 + (j & 7) * 16;
+      *reinterpret_cast<uint4*>(sK + off) = hi;
+      *reinterpret_cast<uint4*>(sK + kAcPartK + off) = lo;
+    }
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {                               // V^T: element (d, key j)
+      const __half hi = __float2half_rn(vf[d]);
+      const __half lo = __float2half_rn(vf[d] - __half2float(hi));
+      const uint32_t off = (d >> 3) * kAcSboV + (j >> 3) * 128 + (d & 7) * 16 + (j & 7) * 2;
+      *reinterpret_cast<__half*>(sV + off) = hi;
+      *reinterpret_cast<__half*>(sV + kAcPartV + off) = lo;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint64_t kdesc = tc::smem_desc(tc::smem_u32(sK), 128, kAcSboK);
+  const uint64_t vdesc = tc::smem_desc(tc::smem_u32(sV), 128, kAcSboV);
+  const uint64_t qdesc = tc::smem_desc(tc::smem_u32(sQ), 128, kAcSboK);
+  const int n1 = Kp < 256 ? Kp : 256, n2 = Kp - n1;              // the score product as one or two MMAs along N
+  const uint32_t idesc1 = tc::idesc_f16(128, n1), idesc2 = tc::idesc_f16(128, n2 > 0 ? n2 : 16), idesc_o = tc::idesc_f16(128, 16);
+
+  const int q4 = warp & 3, ch = warp >> 2;                       // TMEM lane quarter; which half of the key groups
+  const int row = 32 * q4 + lane;
+  const uint32_t lane_sel = static_cast<uint32_t>(32 * q4) << 16;
+  const int g_split = (groups + 1) / 2;
+  const int g_begin = ch == 0 ? 0 : g_split, g_end = ch == 0 ? g_split : groups;
+  uint32_t phase = 0;
+
+  for (int i0 = 0; i0 < Tp; i0 += 128) {
+    // ---- Q tile: row = query i0 + r, scaled to log2 units, hi / lo
+    if (tid < 128) {
+      const int i = i0 + tid;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v8[8];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float4 q4v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < Tp) q4v = __ldg(reinterpret_cast<const float4*>(base + static_cast<long>(i) * 3 * N) + 2 * c + e);
+          v8[4 * e] = q4v.x * scale; v8[4 * e + 1] = q4v.y * scale; v8[4 * e + 2] = q4v.z * scale; v8[4 * e + 3] = q4v.w * scale;
+        }
+        uint4 hi, lo;
+        tc::split_half8(v8, &hi, &lo);
+        const uint32_t off = (tid >> 3) * kAcSboK + c * 128 + (tid & 7) * 16;
+        *reinterpret_cast<uint4*>(sQ + off) = hi;
+        *reinterpret_cast<uint4*>(sQ + kAcPartQ + off) = lo;
+      }
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    // ---- S = Q K^T (K = 16: one step): Qh Kh + Ql Kh + Qh Kl
+    if (warp == 0) {
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint64_t ql = qdesc + (kAcPartQ >> 4), kl = kdesc + (kAcPartK >> 4);
+        tc::mma_ss(tmem, qdesc, kdesc, idesc1, false);
+        tc::mma_ss(tmem, ql, kdesc, idesc1, true);
+        tc::mma_ss(tmem, qdesc, kl, idesc1, true);
+        if (n2 > 0) {
+          const uint64_t koff = static_cast<uint64_t>((256 / 8) * kAcSboK) >> 4;      // key rows 256..
+          tc::mma_ss(tmem + 256, qdesc, kdesc + koff, idesc2, false);
+          tc::mma_ss(tmem + 256, ql, kdesc + koff, idesc2, true);
+          tc::mma_ss(tmem + 256, qdesc, kl + koff, idesc2, true);
+        }
+        tc::commit(&bar);
+      }
+    }
+    tc::mbar_wait(&bar, phase & 1);
+    ++phase;
+    tc::fence_after_sync();
+    // ---- pass 1: row maximum over this warp's key groups
+    float mx = -INFINITY;
+    for (int g = g_begin; g < g_end; ++g) {
+      uint32_t v[16];
+      tc::ld16(tmem + lane_sel + 16 * g, v);
+      tc::wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (16 * g + e < Tp) mx = fmaxf(mx, __uint_as_float(v[e]));
+    }
+    sMax[ch][row] = mx;
+    __syncthreads();
+    mx = fmaxf(sMax[0][row], sMax[1][row]);
+    // ---- pass 2: p = 2^(s - max) back into the same columns as the A operand of the next product (hi | lo per key group)
+    float sum = 0.0f;
+    for (int g = g_begin; g < g_end; ++g) {
+      uint32_t v[16];
+      tc::ld16(tmem + lane_sel + 16 * g, v);
+      tc::wait_ld();
+      uint32_t ph[8], pl[8];
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        float p0 = 0.0f, p1 = 0.0f;
+        if (16 * g + e < Tp) p0 = exp2f(__uint_as_float(v[e]) - mx);
+        if (16 * g + e + 1 < Tp) p1 = exp2f(__uint_as_float(v[e + 1]) - mx);
+        sum += p0 + p1;
+        const __half2 hh = __floats2half2_rn(p0, p1);
+        const float2 bb = __half22float2(hh);
+        ph[e / 2] = *reinterpret_cast<const uint32_t*>(&hh);
+        pl[e / 2] = tc::pack_half2(p0 - bb.x, p1 - bb.y);
+      }
+      tc::st8(tmem + lane_sel + 16 * g, ph);
+      tc::st8(tmem + lane_sel + 16 * g + 8, pl);
+    }
+    sSum[ch][row] = sum;
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    // ---- O = P V: per key group  Ph Vh + Pl Vh + Ph Vl
+    if (warp == 0) {
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint64_t vl = vdesc + (kAcPartV >> 4);
+        for (int g = 0; g < groups; ++g) {
+          const uint64_t step = static_cast<uint64_t>(g) * ((2 * 128) >> 4);
+          tc::mma_ts(tmem + kAcColO, tmem + 16 * g, vdesc + step, idesc_o, g > 0);
+          tc::mma_ts(tmem + kAcColO, tmem + 16 * g + 8, vdesc + step, idesc_o, true);
+          tc::mma_ts(tmem + kAcColO, tmem + 16 * g, vl + step, idesc_o, true);
+        }
+        tc::commit(&bar);
+      }
+    }
+    tc::mbar_wait(&bar, phase & 1);
+    ++phase;
+    tc::fence_after_sync();
+    if (ch == 0) {
+      uint32_t v[16];
+      tc::ld16(tmem + lane_sel + kAcColO, v);
+      tc::wait_ld();
+      const int i = i0 + row;
+      if (i < Tp) {
+        const float inv = 1.0f / (sSum[0][row] + sSum[1][row]);
+        float4* dst = reinterpret_cast<float4*>(out + (b * Tp + i) * N + h * kAcD);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_float4(__uint_as_float(v[4 * c]) * inv, __uint_as_float(v[4 * c + 1]) * inv,
+                               __uint_as_float(v[4 * c + 2]) * inv, __uint_as_float(v[4 * c + 3]) * inv);
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();                              // the tile's TMEM columns and sQ are reused by the next tile
+    tc::fence_after_sync();
+  }
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+bool att_core_tc_supported(int Tp, int heads, int hidden) { return Tp >= 1 && Tp <= kAcMaxKeys && hidden == heads * kAcD; }
+
+int launch_att_core_tc(const float* qkv, long B, int Tp, int heads, float* out, cudaStream_t st) {
+  if (B <= 0) return KWS_OK;
+  constexpr int smem = 2 * kAcPartK + 2 * kAcPartV + 2 * kAcPartQ;
+  KWS_CUDA_OK(cudaFuncSetAttribute(att_core_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  att_core_tc_kernel<<<static_cast<unsigned>(B * heads), kAcThreads, smem, st>>>(qkv, Tp, heads, out);
+  KWS_LAUNCH_OK("att_core_tc_kernel");
+  return KWS_OK;
+}
+
 }  // namespace kws

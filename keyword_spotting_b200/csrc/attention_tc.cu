@@ -222,6 +222,12 @@ constexpr int kAcPartV = 2 * kAcSboV;            // 12800
 constexpr int kAcPartQ = (128 / 8) * kAcSboK;    // 4096
 constexpr int kAcColO = kAcMaxKeys;
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kAcThreads, 1)
 att_core_tc_kernel(const float* __restrict__ qkv, int Tp, int heads, float* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -336,39 +342,54 @@ att_core_tc_kernel(const float* __restrict__ qkv, int Tp, int heads, float* __re
     tc::mbar_wait(&bar, phase & 1);
     ++phase;
     tc::fence_after_sync();
+    // (a warp whose 32 query rows all lie past T' -- three of the four lane quarters of the last tile -- skips both passes:
+    // its rows of P stay garbage, which only reaches its own, never stored, rows of O)
+    const bool warp_live = i0 + 32 * q4 < Tp;
+    const int g_tail = (Tp & 15) ? groups - 1 : groups;          // the one key group with padded keys, if any
     // ---- pass 1: row maximum over this warp's key groups
     float mx = -INFINITY;
-    for (int g = g_begin; g < g_end; ++g) {
-      uint32_t v[16];
-      tc::ld16(tmem + lane_sel + 16 * g, v);
-      tc::wait_ld();
+    if (warp_live) {
+      for (int g = g_begin; g < g_end; ++g) {
+        uint32_t v[16];
+        tc::ld16(tmem + lane_sel + 16 * g, v);
+        tc::wait_ld();
+        if (g < g_tail) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (16 * g + e < Tp) mx = fmaxf(mx, __uint_as_float(v[e]));
+          for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (16 * g + e < Tp) mx = fmaxf(mx, __uint_as_float(v[e]));
+        }
+      }
     }
     sMax[ch][row] = mx;
     __syncthreads();
     mx = fmaxf(sMax[0][row], sMax[1][row]);
     // ---- pass 2: p = 2^(s - max) back into the same columns as the A operand of the next product (hi | lo per key group)
     float sum = 0.0f;
-    for (int g = g_begin; g < g_end; ++g) {
-      uint32_t v[16];
-      tc::ld16(tmem + lane_sel + 16 * g, v);
-      tc::wait_ld();
-      uint32_t ph[8], pl[8];
+    if (warp_live) {
+      for (int g = g_begin; g < g_end; ++g) {
+        uint32_t v[16];
+        tc::ld16(tmem + lane_sel + 16 * g, v);
+        tc::wait_ld();
+        uint32_t ph[8], pl[8];
 #pragma unroll
-      for (int e = 0; e < 16; e += 2) {
-        float p0 = 0.0f, p1 = 0.0f;
-        if (16 * g + e < Tp) p0 = exp2f(__uint_as_float(v[e]) - mx);
-        if (16 * g + e + 1 < Tp) p1 = exp2f(__uint_as_float(v[e + 1]) - mx);
-        sum += p0 + p1;
-        const __half2 hh = __floats2half2_rn(p0, p1);
-        const float2 bb = __half22float2(hh);
-        ph[e / 2] = *reinterpret_cast<const uint32_t*>(&hh);
-        pl[e / 2] = tc::pack_half2(p0 - bb.x, p1 - bb.y);
+        for (int e = 0; e < 16; e += 2) {
+          float p0 = ex2_fast(__uint_as_float(v[e]) - mx), p1 = ex2_fast(__uint_as_float(v[e + 1]) - mx);
+          if (g >= g_tail) {                                     // padded keys carry no weight
+            if (16 * g + e >= Tp) p0 = 0.0f;
+            if (16 * g + e + 1 >= Tp) p1 = 0.0f;
+          }
+          sum += p0 + p1;
+          const __half2 hh = __floats2half2_rn(p0, p1);
+          const float2 bb = __half22float2(hh);
+          ph[e / 2] = *reinterpret_cast<const uint32_t*>(&hh);
+          pl[e / 2] = tc::pack_half2(p0 - bb.x, p1 - bb.y);
+        }
+        tc::st8(tmem + lane_sel + 16 * g, ph);
+        tc::st8(tmem + lane_sel + 16 * g + 8, pl);
       }
-      tc::st8(tmem + lane_sel + 16 * g, ph);
-      tc::st8(tmem + lane_sel + 16 * g + 8, pl);
     }
     sSum[ch][row] = sum;
     tc::wait_st();

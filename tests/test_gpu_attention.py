@@ -17,7 +17,11 @@ def att():
     m.close()
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (1, 2), (2, 37), (3, 100), (1, 255), (2, 798), (5, 256)])
+# T' = T // 2 + 1 keys.  The tensor-core attention core takes T' <= 400: 510 -> 256 keys (one score MMA), 512 -> 257 keys
+# (padded to 272: a second MMA of 16 columns), 766 -> 384 (whole query tiles), 798 -> 400 (the full TMEM budget);
+# 1000 -> 501 keys runs the FFMA attention core behind the tensor-core dense layers.
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 2), (2, 37), (3, 100), (1, 255), (2, 798), (5, 256), (1, 510), (2, 512), (3, 766),
+                                 (2, 1000)])
 def test_attention_mel_forward_matches_oracle(att, B, T):
     from oracle import attention as oa
     ow, m = att

@@ -194,23 +194,52 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 __global__ void __launch_bounds__(1024)
 att_add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
-                         const float* __restrict__ beta, int Tp, int N, float* __restrict__ y) {
+                         const float* __restrict__ beta, int Tp, int N, int in_smem, float* __restrict__ y) {
+  // the utterance's a + b is kept in shared memory when it fits (T' * N <= 51,200 floats: 8 s at config 5), so a and b
+  // are read from HBM once and the mean / variance / output passes run out of shared memory; N % 4 == 0
+  extern __shared__ __align__(16) float sx[];
   __shared__ float red[32];
   const long base = blockIdx.x * static_cast<long>(Tp) * N;
-  const int n = Tp * N;
+  const int n = Tp * N, n4 = n >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(a + base);
+  const float4* b4 = reinterpret_cast<const float4*>(b + base);
+  float4* s4 = reinterpret_cast<float4*>(sx);
   float s = 0.0f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += a[base + i] + b[base + i];
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 u = __ldg(a4 + i), w = __ldg(b4 + i);
+    const float4 t = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
+    if (in_smem) s4[i] = t;
+    s += (t.x + t.y) + (t.z + t.w);
+  }
   const float mean = block_sum(s, red) / n;
   float v = 0.0f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = a[base + i] + b[base + i] - mean;
-    v = fmaf(d, d, v);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 t;
+    if (in_smem) {
+      t = s4[i];
+    } else {
+      const float4 u = __ldg(a4 + i), w = __ldg(b4 + i);
+      t = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
+    }
+    const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
+    v = fmaf(d0, d0, v); v = fmaf(d1, d1, v); v = fmaf(d2, d2, v); v = fmaf(d3, d3, v);
   }
   const float var = block_sum(v, red) / n;
   const float inv = 1.0f / sqrtf(var + 1e-12f);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int c = i % N;
-    y[base + i] = (a[base + i] + b[base + i] - mean) * inv * gamma[c] + beta[c];
+  float4* y4 = reinterpret_cast<float4*>(y + base);
+  const int nq = N >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 t;
+    if (in_smem) {
+      t = s4[i];
+    } else {
+      const float4 u = __ldg(a4 + i), w = __ldg(b4 + i);
+      t = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
+    }
+    const int c = (i % nq) << 2;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    y4[i] = make_float4((t.x - mean) * inv * g.x + be.x, (t.y - mean) * inv * g.y + be.y, (t.z - mean) * inv * g.z + be.z,
+                        (t.w - mean) * inv * g.w + be.w);
   }
 }
 
@@ -402,6 +431,11 @@ extern "C" int kws_attention_forward(kws_attention* m, const float* mel, int64_t
   float* att = y + static_cast<size_t>(rows) * N;
   float* big = att + static_cast<size_t>(rows) * N;
 
+  // layer norm: the utterance's T' * N floats in shared memory when they fit
+  const size_t ln_bytes = sizeof(float) * static_cast<size_t>(Tp) * N;
+  const int ln_in_smem = ln_bytes <= 200 * 1024 ? 1 : 0;
+  const size_t ln_smem = ln_in_smem ? ln_bytes : 0;
+  KWS_CUDA_OK(cudaFuncSetAttribute(att_add_layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const long total_in = rows * Kin;
   att_combine_kernel<<<static_cast<unsigned>(ceil_div(total_in, 256)), 256, 0, st>>>(mel, B, T, c.n_mel, c.combine_frame, Tp, xin);
   KWS_LAUNCH_OK("att_combine_kernel");
@@ -418,12 +452,12 @@ extern "C" int kws_attention_forward(kws_attention* m, const float* mel, int64_t
       att_attention_kernel<<<ga, 128, 0, st>>>(big, Tp, c.heads, att);
       KWS_LAUNCH_OK("att_attention_kernel");
     }
-    att_add_layernorm_kernel<<<static_cast<unsigned>(B), 1024, 0, st>>>(att, x, L.ln1_g, L.ln1_b, Tp, N, y);
+    att_add_layernorm_kernel<<<static_cast<unsigned>(B), 1024, ln_smem, st>>>(att, x, L.ln1_g, L.ln1_b, Tp, N, ln_in_smem, y);
     KWS_LAUNCH_OK("att_add_layernorm_kernel");
     rc = att_linear<true, false>(y, L.w_ff1, m->p_ff1[l], L.b_ff1, nullptr, Tp, rows, N, F, big, st);
     if (rc == KWS_OK) rc = att_linear<false, false>(big, L.w_ff2, m->p_ff2[l], L.b_ff2, nullptr, Tp, rows, F, N, att, st);
     if (rc != KWS_OK) break;
-    att_add_layernorm_kernel<<<static_cast<unsigned>(B), 1024, 0, st>>>(att, y, L.ln2_g, L.ln2_b, Tp, N, x);
+    att_add_layernorm_kernel<<<static_cast<unsigned>(B), 1024, ln_smem, st>>>(att, y, L.ln2_g, L.ln2_b, Tp, N, ln_in_smem, x);
     KWS_LAUNCH_OK("att_add_layernorm_kernel");
   }
   if (rc != KWS_OK) return rc;

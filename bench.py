@@ -832,10 +832,12 @@ def run_attention(args, rank, world, local_rank):
                                 utterances_per_gpu=B, sharding="utterances/dp%d" % world,
                                 l2_policy="inputs larger than L2: 2 rotating %.0f MB PCM buffers" % (B * L * 2 / 1e6)),
                     utterances_per_s=world * B * args.steps / (total_ms * 1e-3),
-                    roofline=dict(kernel="att_linear_kernel + att_attention_kernel (fp32 FFMA)", bound="tensor",
+                    roofline=dict(kernel="att_linear_tc_kernel + att_core_tc_kernel (tcgen05 kind::f16, fp16 hi/lo operand splits)", bound="tensor",
                                   achieved=flop * args.steps / (total_ms * 1e-3) / 1e12, peak=peaks["bf16"], unit="TFLOP/s",
                                   frac=flop * args.steps / (total_ms * 1e-3) / 1e12 / peaks["bf16"], traffic=None,
-                                  note="0.69 GFLOP per utterance; the contractions run on the CUDA cores (fp32), see DESIGN.md"),
+                                  note="algorithmic 0.69 GFLOP per utterance over the whole step (front end, layer norm and softmax passes included); "
+                                       "every contraction runs as three fp16 MMAs (x_hi w_hi + x_lo w_hi + x_hi w_lo) for fp32-grade results, "
+                                       "so the tensor pipe executes 3x the algorithmic FLOP; see DESIGN.md"),
                     e2e=dict(value=audio / (e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * L * 2, d2h_bytes_per_step=B * Tp * 6 * 4,
                              ms_per_step=e_ms / args.steps,
                              note="pinned host int16 PCM -> H2D -> AttentionDeployModel call -> D2H softmax, every step"),

@@ -664,6 +664,7 @@ def run_ours(args, rank, world, local_rank):
     # the roofline of the dominant kernel (largest launch time); the others alongside
     roofline, roofline_other = (roof_fe, [roof_gru, roof_post]) if fe_launch_ms >= gru_launch_ms else (roof_gru, [roof_fe, roof_post])
     del pcm_full, mel, probs, st
+    torch.cuda.empty_cache()                         # the library allocates with cudaMalloc: hand torch's cached blocks back
 
     # ---- end to end through the package's wave server (kws_server_*): pinned host PCM -> H2D -> step -> D2H flags
     e2e = None

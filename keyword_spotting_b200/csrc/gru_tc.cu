@@ -42,6 +42,11 @@
 // dropped lo*lo term is 2^-22 relative), i.e. at fp32-grade accuracy for +6 small MMAs per step: the front end
 // writes both halves of the split.  With it the deviation from the fp32 graph stays below 1e-3 (contract) on
 // probabilities and state; see DESIGN.md.
+//
+// Build-time experiment switches (tools/build_variant.sh <name> gru_tc.cu -D...; select the result with KWS_B200_LIB):
+//   KWS_ABL_NOX1, KWS_ABL_NOLO  ablations -- drop layer 1's x loads/stores or the lo halves of h' to TIME what they cost
+//                               (the results are wrong by construction);  KWS_L2_PREFETCH=<steps>  bulk L2 prefetch of layer
+//                               1's x that many steps ahead (measured: -1 %, off by default).
 #include <type_traits>
 #include <vector>
 

@@ -653,7 +653,13 @@ def run_ours(args, rank, world, local_rank):
                    algorithmic_bytes=S * FE_BYTES_PER_STREAM_CHUNK, traffic_source=traffic.get("_source"),
                    peak_source=peaks["source"] + ", copy bandwidth",
                    note="algorithmic bytes = %d per stream-chunk (int16 PCM in, carried tail r+w, fp32 mel out, flags); "
-                        "one launch per step; timed inside the production step (fused VAD/tail work included)" % FE_BYTES_PER_STREAM_CHUNK)
+                        "one launch per step; timed inside the production step (fused VAD/tail work included)" % FE_BYTES_PER_STREAM_CHUNK,
+                   limiter=("HBM is the bound by contract (SURVEY.md 8d), not in fact: DRAM traffic equals the algorithmic bytes, and ncu shows the "
+                            "400-point FFT's shared-memory transposition at 72 % of the LSU wavefront peak with 50 % of the issue slots in use "
+                            "(profiles/r02_ncu_summary_v11.md); the tensor-core formulation of the same transform reaches the same time "
+                            "(profiles/r02_frontend_tc.md)") if args.frontend == "fft" else
+                           "TMEM capacity: one accumulator buffer, transforms and combination of consecutive items cannot overlap "
+                           "(profiles/r02_frontend_tc.md)")
     post_gbs = S * POST_BYTES_PER_STREAM_CHUNK / (max(parts[2], 1e-6) * 1e-3) / 1e9
     roof_post = dict(kernel="stream_post_kernel", bound="hbm", achieved=post_gbs, peak=peaks["hbm"], unit="GB/s",
                      frac=post_gbs / peaks["hbm"], traffic=traffic.get("stream_post_kernel"), launch_ms=parts[2],

@@ -55,19 +55,15 @@ att_linear_tc_kernel(const float* __restrict__ A, const unsigned char* __restric
   const uint64_t adesc = tc::smem_desc(tc::smem_u32(sA), kAlLboA, kAlSboA);
   const uint64_t wdesc = tc::smem_desc(tc::smem_u32(sW), 128, kAlSboW);
 
-  for (int kc = 0; kc < nchunks; ++kc) {
-    if (kc > 0) {                                          // the previous chunk's MMAs have read both buffers
-      tc::mbar_wait(&bar, (kc - 1) & 1);
-      tc::fence_after_sync();
-    }
-    {
-      const uint4* wsrc = reinterpret_cast<const uint4*>(wpack + (static_cast<size_t>(nt) * nchunks + kc) * (2 * kAlPartW));
+  // this thread's eight 16-byte pieces of an A chunk: 16 consecutive threads read the 256 contiguous bytes of a row.  The
+  // pieces of chunk kc + 1 are requested before the MMAs of chunk kc are issued, so HBM latency runs under them.
+  constexpr int kPieces = kAlTile * (kAlKc / 4) / kAlThreads;
+  float4 areg[kPieces];
+  auto load_a = [&](int kc) {
 #pragma unroll
-      for (int i = tid; i < 2 * kAlPartW / 16; i += kAlThreads) reinterpret_cast<uint4*>(sW)[i] = __ldg(wsrc + i);
-    }
-#pragma unroll
-    for (int i = tid; i < kAlTile * (kAlKc / 4); i += kAlThreads) {
-      const int row = i >> 4, q = i & 15;                  // 16 consecutive threads read the 256 contiguous bytes of a row
+    for (int j = 0; j < kPieces; ++j) {
+      const int i = tid + j * kAlThreads;
+      const int row = i >> 4, q = i & 15;
       const int k = kc * kAlKc + 4 * q;
       const long gr = r0 + row;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -81,6 +77,25 @@ att_linear_tc_kernel(const float* __restrict__ A, const unsigned char* __restric
           if (k + 2 < K) v.z = __ldg(src + 2);
         }
       }
+      areg[j] = v;
+    }
+  };
+  load_a(0);
+  for (int kc = 0; kc < nchunks; ++kc) {
+    if (kc > 0) {                                          // the previous chunk's MMAs have read both buffers
+      tc::mbar_wait(&bar, (kc - 1) & 1);
+      tc::fence_after_sync();
+    }
+    {
+      const uint4* wsrc = reinterpret_cast<const uint4*>(wpack + (static_cast<size_t>(nt) * nchunks + kc) * (2 * kAlPartW));
+#pragma unroll
+      for (int i = tid; i < 2 * kAlPartW / 16; i += kAlThreads) reinterpret_cast<uint4*>(sW)[i] = __ldg(wsrc + i);
+    }
+#pragma unroll
+    for (int j = 0; j < kPieces; ++j) {
+      const int i = tid + j * kAlThreads;
+      const int row = i >> 4, q = i & 15;
+      const float4 v = areg[j];
       const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
       const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
       const uint32_t off = (row >> 3) * kAlSboA + (q >> 1) * kAlLboA + (row & 7) * 16 + (q & 1) * 8;
@@ -88,6 +103,7 @@ att_linear_tc_kernel(const float* __restrict__ A, const unsigned char* __restric
       *reinterpret_cast<uint2*>(sA + kAlPartA + off) =
           make_uint2(tc::pack_half2(v.x - b01.x, v.y - b01.y), tc::pack_half2(v.z - b23.x, v.w - b23.y));
     }
+    if (kc + 1 < nchunks) load_a(kc + 1);
     tc::fence_proxy_async();                               // generic-proxy stores -> MMA operand fetch
     tc::fence_before_sync();
     __syncthreads();

@@ -24,7 +24,10 @@ namespace kws {
 
 constexpr int kOctTile = 64;            // streams per CTA = tile of the fp32 kernel's [tile][t][unit][64] hand-off
 constexpr int kOctWarpStreams = 16;     // rows of one mma
-constexpr int kOctThreads = 32 * (kOctTile / kOctWarpStreams);
+constexpr int kOctCtaWarps = 2;          // warps per CTA: 37.6 KB of shared memory per warp -> three 2-warp CTAs (6 warps) per SM
+                                        // instead of one 4-warp CTA; the warps of a tile never talk to each other
+constexpr int kOctThreads = 32 * kOctCtaWarps;
+constexpr int kOctPartsPerTile = (kOctTile / kOctWarpStreams) / kOctCtaWarps;
 constexpr int kOctK = 2 * kHidden;      // [x | h]
 constexpr int kOctAStride = kOctK + 4;  // floats per row of the fp32 vector (bank spread, 16-byte aligned)
 constexpr int kOctQStride = kOctK + 16; // bytes per row of the u8 vector (conflict-free fragment loads)
@@ -136,12 +139,12 @@ __device__ __forceinline__ void oct_mma_chunk(int (&acc)[8][4], const OctMatDev&
 __global__ void __launch_bounds__(kOctThreads)
 gru_octbit_layer_kernel(const GruOctParams p) {
   extern __shared__ __align__(16) unsigned char smem_oct[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per-warp regions (a warp never touches another warp's streams: only __syncwarp inside the time loop)
   constexpr size_t kPerWarp = sizeof(float) * kOctWarpStreams * kOctAStride + kOctWarpStreams * kOctQStride +
                               sizeof(float) * 2 * kOctWarpStreams * kHidden + sizeof(float) * kOctWarpStreams +
                               sizeof(int) * 2 * kOctWarpStreams;
-  unsigned char* base = smem_oct + warp * kPerWarp;
+  unsigned char* base = smem_oct + cta_warp * kPerWarp;
   float* af = reinterpret_cast<float*>(base);                                 // [16][260]  [x | h] then [x | r*h]
   unsigned char* q = reinterpret_cast<unsigned char*>(af + kOctWarpStreams * kOctAStride);   // [16][272]
   float* hs = reinterpret_cast<float*>(q + kOctWarpStreams * kOctQStride);    // [16][128] fp32 state
@@ -152,7 +155,9 @@ gru_octbit_layer_kernel(const GruOctParams p) {
   const int g = lane >> 2, t4 = lane & 3;
   const long ntiles = (p.S + kOctTile - 1) / kOctTile;
 
-  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (long part = blockIdx.x; part < ntiles * kOctPartsPerTile; part += gridDim.x) {
+    const long tile = part / kOctPartsPerTile;
+    const int warp = static_cast<int>(part - tile * kOctPartsPerTile) * kOctCtaWarps + cta_warp;   // this warp's 16 streams of the tile
     const long s_warp = tile * kOctTile + warp * kOctWarpStreams;
     // ---- carried state -> hs
     for (int i = lane; i < kOctWarpStreams * kHidden / 4; i += 32) {
@@ -263,7 +268,7 @@ static size_t gru_octbit_smem_bytes() {
   const size_t per_warp = sizeof(float) * kOctWarpStreams * kOctAStride + kOctWarpStreams * kOctQStride +
                           sizeof(float) * 2 * kOctWarpStreams * kHidden + sizeof(float) * kOctWarpStreams +
                           sizeof(int) * 2 * kOctWarpStreams;
-  return per_warp * (kOctTile / kOctWarpStreams);
+  return per_warp * kOctCtaWarps;
 }
 
 // FC + softmax on the last layer's outputs y [S, n, H]: one warp per stream.
@@ -466,7 +471,8 @@ int launch_gru_octbit(kws_model* m, const GruArgs& a, cudaStream_t st) {
     p.zero_state = a.zero_state;
     const size_t smem = gru_octbit_smem_bytes();
     KWS_CUDA_OK(cudaFuncSetAttribute(gru_octbit_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const long blocks = ntiles < 2L * sm_count() ? ntiles : 2L * sm_count();
+    const long parts = ntiles * kOctPartsPerTile;
+    const long blocks = parts < 3L * sm_count() ? parts : 3L * sm_count();
     gru_octbit_layer_kernel<<<static_cast<unsigned>(blocks), kOctThreads, smem, st>>>(p);
     KWS_LAUNCH_OK("gru_octbit_layer_kernel");
   }
